@@ -1,0 +1,159 @@
+"""hj3d_b200 -- Python front-end (tests / bench plumbing) of the B200-native 3D hash-join engine.
+
+The product is ``lib/libhj3d.so`` (hand-written sm_100a CUDA behind the C ABI of ``include/hj3d.h``)
+plus the C++20 operator templates in ``hostcpp/hj3d/`` that mirror the reference's ``algebra.hh``.
+This module only wraps the C ABI for callers that hold their relations in torch CUDA tensors.
+The directory name is not an importable identifier; load it through ``hj3d_loader`` at the repo root.
+"""
+import ctypes as C
+
+from . import capi
+from .capi import (CHAINING, F_CHECKSUM, HASH_MURMUR32, HASH_MURMUR64, HASH_MURMUR64_SEXT32, NESTED, NO_ROWID,
+                   OPT_PARTITION_BYTES, OPT_PARTITION_WINDOW, OPT_WARP_AGGREGATE, Counters, Hj3dError, KeySpec,
+                   Stats, Timings)
+
+__all__ = ["Context", "Table", "KeySpec", "Hj3dError", "CHAINING", "NESTED", "F_CHECKSUM", "capi"]
+
+
+def _ptr(t):
+    """device pointer of a torch tensor / raw int / None"""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """hj3d_ctx: one device, one stream."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        capi.check(self.lib.hj3d_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        if stream is not None:
+            # torch reports the legacy default stream as 0; the C ABI takes NULL as "ctx-owned stream",
+            # so name the default stream by its CUDA handle cudaStreamLegacy (0x1)
+            stream = int(stream) or 1
+            capi.check(self.lib.hj3d_ctx_set_stream(self.h, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hj3d_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, opt, value):
+        capi.check(self.lib.hj3d_ctx_set_option(self.h, opt, int(value)))
+
+    def sync(self):
+        capi.check(self.lib.hj3d_ctx_sync(self.h))
+
+    def timings(self):
+        t = Timings()
+        capi.check(self.lib.hj3d_ctx_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def table(self, kind, num_buckets, shard=None):
+        return Table(self, kind, num_buckets, shard)
+
+    # -- column helpers ------------------------------------------------------------------------
+    def split_pairs(self, pairs, n, left, right):
+        capi.check(self.lib.hj3d_split_pairs(self.h, _ptr(pairs), n, _ptr(left), _ptr(right)))
+
+    def gather_u32(self, src, idx, n, dst):
+        capi.check(self.lib.hj3d_gather_u32(self.h, _ptr(src), _ptr(idx), n, _ptr(dst)))
+
+    def partition_by_owner(self, tuples, n, ks, num_buckets, n_owners, rowid_base, out):
+        counts = (C.c_uint64 * n_owners)()
+        capi.check(self.lib.hj3d_partition_by_owner(self.h, _ptr(tuples), n, ks, num_buckets, n_owners, rowid_base,
+                                                    _ptr(out), counts))
+        return [int(x) for x in counts]
+
+    def join_host(self, mode, h_build, n_build, ks_build, num_buckets, h_probe, n_probe, ks_probe,
+                  flags=0, h_out=None, out_cap=0, want_stats=False):
+        """hj3d_join_host on host buffers (numpy arrays / pinned torch CPU tensors / raw addresses)."""
+        def hp(a):
+            if a is None:
+                return None
+            if isinstance(a, int):
+                return C.c_void_p(a)
+            if hasattr(a, "data_ptr"):
+                return C.c_void_p(a.data_ptr())
+            return a.ctypes.data_as(C.c_void_p)
+        pc, uc, st = Counters(), Counters(), Stats()
+        rc = capi.check(self.lib.hj3d_join_host(self.h, mode, hp(h_build), n_build, ks_build, num_buckets,
+                                                hp(h_probe), n_probe, ks_probe, flags, hp(h_out), out_cap,
+                                                C.byref(pc), C.byref(uc), C.byref(st) if want_stats else None))
+        return rc, pc.as_dict(), uc.as_dict(), (st.as_dict() if want_stats else None)
+
+
+class Table:
+    """hj3d_table: the chaining (HtChaining1) or nested (HtNested1) table of one build operator."""
+
+    def __init__(self, ctx, kind, num_buckets, shard=None):
+        self.ctx, self.lib, self.kind = ctx, ctx.lib, kind
+        h = C.c_void_p()
+        if shard is None:
+            capi.check(self.lib.hj3d_table_create(ctx.h, kind, int(num_buckets), C.byref(h)))
+        else:
+            capi.check(self.lib.hj3d_table_create_shard(ctx.h, kind, int(num_buckets), int(shard[0]), int(shard[1]),
+                                                        C.byref(h)))
+        self.h = h
+
+    def destroy(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.lib.hj3d_table_destroy(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def build(self, tuples, n, ks):
+        capi.check(self.lib.hj3d_table_build(self.ctx.h, self.h, _ptr(tuples), int(n), ks))
+        return self
+
+    def clear(self):
+        capi.check(self.lib.hj3d_table_clear(self.ctx.h, self.h))
+
+    def stats(self):
+        s = Stats()
+        capi.check(self.lib.hj3d_table_stats(self.ctx.h, self.h, C.byref(s)))
+        return s.as_dict()
+
+    def size(self):
+        n, g = C.c_uint64(), C.c_uint64()
+        capi.check(self.lib.hj3d_table_size(self.h, C.byref(n), C.byref(g)))
+        return int(n.value), int(g.value)
+
+    def probe_chaining(self, tuples, n, ks, unique=False, gather=None, flags=F_CHECKSUM, out=None, out_cap=0):
+        c = Counters()
+        rc = capi.check(self.lib.hj3d_probe_chaining(self.ctx.h, self.h, _ptr(tuples), int(n), ks, _ptr(gather),
+                                                     int(bool(unique)), flags, _ptr(out), int(out_cap), C.byref(c)))
+        return rc, c.as_dict()
+
+    def probe_nested(self, tuples, n, ks, gather=None, flags=F_CHECKSUM, out=None, out_cap=0):
+        c = Counters()
+        rc = capi.check(self.lib.hj3d_probe_nested(self.ctx.h, self.h, _ptr(tuples), int(n), ks, _ptr(gather), flags,
+                                                   _ptr(out), int(out_cap), C.byref(c)))
+        return rc, c.as_dict()
+
+    def unnest(self, left, gref, n, flags=F_CHECKSUM, out=None, out_cap=0):
+        c = Counters()
+        rc = capi.check(self.lib.hj3d_unnest(self.ctx.h, self.h, _ptr(left), _ptr(gref), int(n), flags, _ptr(out),
+                                             int(out_cap), C.byref(c)))
+        return rc, c.as_dict()
+
+    def group_first_row(self, gref, n, out):
+        capi.check(self.lib.hj3d_group_first_row(self.ctx.h, self.h, _ptr(gref), int(n), _ptr(out)))

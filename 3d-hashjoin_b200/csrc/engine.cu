@@ -1,0 +1,784 @@
+// engine.cu -- host orchestration + C ABI (include/hj3d.h) of the hj3d engine.
+//
+// No CPU fallback: every entry point needs a usable sm_100 device and fails with HJ3D_ERR_CUDA
+// otherwise.  Memory comes from the device's stream-ordered pool (release threshold = max, so
+// steady-state calls do not hit the OS allocator); all kernels run on the ctx's stream.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "build.cuh"
+#include "common.cuh"
+#include "partition.cuh"
+#include "probe.cuh"
+#include "scan.cuh"
+
+using namespace hj3d;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(HJ3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+  } while (0)
+
+#define HJ_TRY(expr) do { int _rc = (expr); if (_rc < 0) return _rc; } while (0)
+
+// ------------------------------------------------------------------------------------ objects
+enum Phase { PH_PARTITION, PH_HIST, PH_SCAN, PH_SCATTER, PH_GROUP, PH_PROBE, PH_UNNEST, PH_COUNT };
+
+struct hj3d_ctx {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  bool         own_stream = false;
+  cudaMemPool_t pool = nullptr;
+  // options
+  int64_t warp_aggregate = 1;
+  int64_t partition_bytes = 48ll << 20;
+  int64_t partition_window = 16ll << 20;
+  // per-phase events of the last call
+  cudaEvent_t ev[PH_COUNT][2];
+  bool        ev_used[PH_COUNT];
+  cudaEvent_t ev_total[2];
+  uint64_t    launches = 0;
+  // small device scratch: counters + stats + scalar, and its pinned host mirror
+  DevCounters* d_ctr = nullptr;
+  DevStats*    d_stats = nullptr;
+  unsigned long long* d_scalar = nullptr;   // 4 scalars
+  void*        h_pinned = nullptr;          // >= 256 B
+  int          sm_count = 148;
+};
+
+struct hj3d_table {
+  int      kind = 0;
+  uint64_t D = 0, blo = 0, bhi = 0;        // global bucket count and owned range
+  Dir      dir{};
+  bool     built = false;
+  int      hash_id = -1;
+  uint32_t key_bytes = 0;
+  uint64_t n = 0, n_groups = 0;
+  uint32_t* off = nullptr;                 // [n_local + 1] bucket run starts
+  void*     slots = nullptr;               // Slot<KeyT>[n]     (chaining; temporary for nested)
+  uint32_t* goff = nullptr;                // [n_local + 1]     (nested)
+  void*     groups = nullptr;              // Group<KeyT>[G]    (nested)
+  uint32_t* rows = nullptr;                // [n]               (nested)
+  DevStats  hstats{};                      // bucket statistics captured during the build
+  bool      have_stats = false;
+};
+
+namespace {
+
+struct PhaseTimer {
+  hj3d_ctx* c; Phase p;
+  PhaseTimer(hj3d_ctx* c_, Phase p_) : c(c_), p(p_) {
+    if (!c->ev_used[p]) { cudaEventRecord(c->ev[p][0], c->stream); c->ev_used[p] = true; }
+  }
+  ~PhaseTimer() { cudaEventRecord(c->ev[p][1], c->stream); }
+};
+
+inline void begin_call(hj3d_ctx* c) {
+  for (int i = 0; i < PH_COUNT; ++i) c->ev_used[i] = false;
+  cudaEventRecord(c->ev_total[0], c->stream);
+}
+inline void end_call(hj3d_ctx* c) { cudaEventRecord(c->ev_total[1], c->stream); }
+
+template <class T> int dev_alloc(hj3d_ctx* c, T** p, uint64_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), c->stream);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(HJ3D_ERR_NOMEM, "device out of memory"); }
+  if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+  return HJ3D_OK;
+}
+inline void dev_free(hj3d_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
+
+inline uint32_t blocks_for(uint64_t n, uint32_t per_block) { return (uint32_t)((n + per_block - 1) / per_block); }
+
+inline int check_keyspec(const hj3d_keyspec& ks) {
+  if (ks.hash_id > 2) return fail(HJ3D_ERR_UNSUPPORTED, "unknown hash_id");
+  const uint32_t kb = ks.hash_id == HJ3D_HASH_MURMUR64 ? 8 : 4;
+  if (ks.key_bytes != kb) return fail(HJ3D_ERR_INVALID, "key_bytes does not match hash_id");
+  if (ks.tuple_bytes == 0 || ks.key_offset + kb > ks.tuple_bytes) return fail(HJ3D_ERR_INVALID, "key outside tuple");
+  if (ks.key_offset % kb || ks.tuple_bytes % kb)
+    return fail(HJ3D_ERR_UNSUPPORTED, "key must be naturally aligned inside the row-store tuple");
+  if (ks.rowid_offset != HJ3D_NO_ROWID && (ks.rowid_offset % 4 || ks.rowid_offset + 4 > ks.tuple_bytes))
+    return fail(HJ3D_ERR_INVALID, "rowid_offset outside tuple / misaligned");
+  return HJ3D_OK;
+}
+
+inline Src make_src(const void* d_tuples, uint64_t n, const hj3d_keyspec& ks, const uint32_t* gather) {
+  Src s; s.base = (const uint8_t*)d_tuples; s.gather = gather; s.n = n; s.stride = ks.tuple_bytes;
+  s.key_off = ks.key_offset; s.rowid_off = ks.rowid_offset;
+  return s;
+}
+
+// ---- scan drivers ---------------------------------------------------------------------------------
+template <class T, bool STATS, class Loader, class Storer>
+int run_scan(hj3d_ctx* c, Loader load, Storer store, uint64_t n, DevStats* d_stats, T* d_total) {
+  const uint32_t nb = blocks_for(n, kScanTile);
+  T* sums = nullptr;
+  HJ_TRY(dev_alloc(c, &sums, nb));
+  k_scan_reduce<T, Loader, STATS><<<nb, kScanThreads, 0, c->stream>>>(load, n, sums, d_stats);
+  k_scan_blocksums<T><<<1, 1024, 0, c->stream>>>(sums, nb, d_total);
+  k_scan_apply<T, Loader, Storer><<<nb, kScanThreads, 0, c->stream>>>(load, store, n, sums);
+  c->launches += 3;
+  dev_free(c, sums);
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+struct LoadU32 { const uint32_t* p; __device__ uint32_t operator()(uint64_t i) const { return p[i]; } };
+struct StoreInclU32 { uint32_t* p; __device__ void operator()(uint64_t i, uint32_t ex, uint32_t v) const { p[i] = ex + v; } };
+
+struct LoadCells {  // packed (claimed ? 1 : 0, gcnt); element n is the sentinel
+  const uint32_t* cell; const uint32_t* gcnt; uint64_t n;
+  __device__ unsigned long long operator()(uint64_t i) const {
+    if (i >= n) return 0ull;
+    return ((unsigned long long)(cell[i] != kEmpty32) << 32) | (unsigned long long)gcnt[i];
+  }
+};
+struct StoreCells {
+  uint32_t* gidx; uint32_t* gstart;
+  __device__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const {
+    gidx[i] = (uint32_t)(ex >> 32); gstart[i] = (uint32_t)ex;
+  }
+};
+struct LoadDiff { const uint32_t* p; __device__ uint32_t operator()(uint64_t i) const { return p[i + 1] - p[i]; } };
+struct StoreNone { __device__ void operator()(uint64_t, uint32_t, uint32_t) const {} };
+
+template <class KeyT> struct LoadGroupLen {
+  const Group<KeyT>* groups; const uint32_t* gref; uint64_t n;
+  __device__ unsigned long long operator()(uint64_t i) const { return i < n ? (unsigned long long)groups[gref[i]].len : 0ull; }
+};
+struct StoreExU64 { unsigned long long* p; __device__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const { p[i] = ex; } };
+
+void init_dev_stats_host(DevStats& s) {
+  s.all = DevAgg{~0ull, 0, 0, 0, 0}; s.nonempty = DevAgg{~0ull, 0, 0, 0, 0}; s.empty = 0;
+}
+
+void free_table_arrays(hj3d_ctx* c, hj3d_table* t) {
+  dev_free(c, t->off); dev_free(c, t->slots); dev_free(c, t->goff); dev_free(c, t->groups); dev_free(c, t->rows);
+  t->off = nullptr; t->slots = nullptr; t->goff = nullptr; t->groups = nullptr; t->rows = nullptr;
+  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false;
+}
+
+// ---- build ----------------------------------------------------------------------------------------
+template <int HASH>
+int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
+  using KeyT = typename HashT<HASH>::key_t;
+  const uint64_t n = src.n;
+  const uint32_t nl = t->dir.n_local;
+  const Dir d = t->dir;
+  const bool agg = c->warp_aggregate != 0;
+  HJ_TRY(dev_alloc(c, &t->off, (uint64_t)nl + 1));
+  Slot<KeyT>* slots = nullptr;
+  HJ_TRY(dev_alloc(c, &slots, n));
+  t->slots = slots;
+  DevStats hs; init_dev_stats_host(hs);
+  CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));  // hs copied synchronously into the driver's staging
+  {
+    PhaseTimer pt(c, PH_HIST);
+    CUDA_TRY(cudaMemsetAsync(t->off, 0, ((uint64_t)nl + 1) * 4, c->stream));
+    if (n) {
+      if (agg) k_histogram<HASH, true><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off);
+      else     k_histogram<HASH, false><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off);
+      ++c->launches;
+    }
+  }
+  {
+    PhaseTimer pt(c, PH_SCAN);
+    // chaining statistics are a function of the bucket histogram alone
+    const bool want_stats = t->kind == HJ3D_CHAINING;
+    if (want_stats) HJ_TRY((run_scan<uint32_t, true>(c, LoadU32{t->off}, StoreInclU32{t->off}, nl, c->d_stats, (uint32_t*)nullptr)));
+    else            HJ_TRY((run_scan<uint32_t, false>(c, LoadU32{t->off}, StoreInclU32{t->off}, nl, (DevStats*)nullptr, (uint32_t*)nullptr)));
+    const uint32_t n32 = (uint32_t)n;
+    CUDA_TRY(cudaMemcpyAsync(t->off + nl, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  {
+    PhaseTimer pt(c, PH_SCATTER);
+    if (n) {
+      if (agg) k_scatter<HASH, true><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off, slots);
+      else     k_scatter<HASH, false><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off, slots);
+      ++c->launches;
+    }
+  }
+  t->n = n;
+  if (t->kind == HJ3D_NESTED) {
+    PhaseTimer pt(c, PH_GROUP);
+    uint32_t *cell = nullptr, *rep = nullptr, *gcnt = nullptr, *gmin = nullptr, *gidx = nullptr, *gstart = nullptr;
+    HJ_TRY(dev_alloc(c, &cell, n)); HJ_TRY(dev_alloc(c, &rep, n)); HJ_TRY(dev_alloc(c, &gcnt, n));
+    HJ_TRY(dev_alloc(c, &gmin, n)); HJ_TRY(dev_alloc(c, &gidx, n + 1)); HJ_TRY(dev_alloc(c, &gstart, n + 1));
+    CUDA_TRY(cudaMemsetAsync(cell, 0xFF, (n ? n : 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(gmin, 0xFF, (n ? n : 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(gcnt, 0, (n ? n : 1) * 4, c->stream));
+    if (n) {
+      k_group_claim<HASH><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, n, d, t->off, cell, rep, gcnt, gmin);
+      ++c->launches;
+    }
+    unsigned long long* d_tot = c->d_scalar;
+    HJ_TRY((run_scan<unsigned long long, false>(c, LoadCells{cell, gcnt, n}, StoreCells{gidx, gstart}, n + 1,
+                                                  (DevStats*)nullptr, d_tot)));
+    unsigned long long tot = 0;
+    CUDA_TRY(cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const uint64_t G = tot >> 32;
+    t->n_groups = G;
+    Group<KeyT>* groups = nullptr;
+    HJ_TRY(dev_alloc(c, &groups, G));
+    t->groups = groups;
+    HJ_TRY(dev_alloc(c, &t->goff, (uint64_t)nl + 1));
+    HJ_TRY(dev_alloc(c, &t->rows, n));
+    if (n) {
+      k_group_emit<HASH><<<blocks_for(n, 256), 256, 0, c->stream>>>(slots, n, cell, gcnt, gmin, gidx, gstart, groups);
+      ++c->launches;
+    }
+    k_group_offsets<<<blocks_for((uint64_t)nl + 1, 256), 256, 0, c->stream>>>(t->off, gidx, nl + 1, t->goff);
+    ++c->launches;
+    if (n) {
+      k_group_rows<HASH><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, n, rep, gstart, t->rows);
+      ++c->launches;
+    }
+    // nested statistics: main chain length per bucket = #distinct keys (ht_nested.hh:459-479)
+    uint32_t* dummy = nullptr;
+    const uint32_t nb = blocks_for(nl, kScanTile);
+    HJ_TRY(dev_alloc(c, &dummy, nb));
+    k_scan_reduce<uint32_t, LoadDiff, true><<<nb, kScanThreads, 0, c->stream>>>(LoadDiff{t->goff}, nl, dummy, c->d_stats);
+    ++c->launches;
+    dev_free(c, dummy);
+    dev_free(c, cell); dev_free(c, rep); dev_free(c, gcnt); dev_free(c, gmin); dev_free(c, gidx); dev_free(c, gstart);
+    // the (key,row) slots are only needed for the chaining probe
+    dev_free(c, t->slots); t->slots = nullptr;
+  }
+  CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaGetLastError());
+  t->have_stats = true;
+  t->built = true;
+  return HJ3D_OK;
+}
+
+int fetch_counters(hj3d_ctx* c, hj3d_counters* out, uint64_t out_cap, bool wrote) {
+  DevCounters* h = (DevCounters*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  out->matches = h->matches; out->num_cmps = h->num_cmps;
+  out->checksum_sum = h->checksum_sum; out->checksum_xor = h->checksum_xor;
+  out->out_tuples = h->matches;
+  out->overflow = (wrote && h->out_cursor > out_cap) ? 1 : 0;
+  out->out_written = wrote ? (h->out_cursor > out_cap ? out_cap : h->out_cursor) : 0;
+  return HJ3D_OK;
+}
+
+template <int HASH>
+int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
+  using KeyT = typename HashT<HASH>::key_t;
+  const uint32_t nb = blocks_for(src.n, kProbeTile);
+  if (!nb) return HJ3D_OK;
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  const Slot<KeyT>* slots = (const Slot<KeyT>*)t->slots;
+#define LAUNCH_PC(U, C, W) k_probe_chaining<HASH, U, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, t->off, slots, out, cap, c->d_ctr)
+  if (unique) { if (cs) { if (wr) LAUNCH_PC(true, true, true); else LAUNCH_PC(true, true, false); }
+                else    { if (wr) LAUNCH_PC(true, false, true); else LAUNCH_PC(true, false, false); } }
+  else        { if (cs) { if (wr) LAUNCH_PC(false, true, true); else LAUNCH_PC(false, true, false); }
+                else    { if (wr) LAUNCH_PC(false, false, true); else LAUNCH_PC(false, false, false); } }
+#undef LAUNCH_PC
+  ++c->launches;
+  return HJ3D_OK;
+}
+
+template <int HASH>
+int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
+  using KeyT = typename HashT<HASH>::key_t;
+  const uint32_t nb = blocks_for(src.n, kProbeTile);
+  if (!nb) return HJ3D_OK;
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
+#define LAUNCH_PN(C, W) k_probe_nested<HASH, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, t->goff, groups, out, cap, c->d_ctr)
+  if (cs) { if (wr) LAUNCH_PN(true, true); else LAUNCH_PN(true, false); }
+  else    { if (wr) LAUNCH_PN(false, true); else LAUNCH_PN(false, false); }
+#undef LAUNCH_PN
+  ++c->launches;
+  return HJ3D_OK;
+}
+
+template <class KeyT>
+int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t* gref, uint64_t n, uint32_t flags,
+                uint2* out, uint64_t cap, hj3d_counters* res) {
+  const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
+  unsigned long long* offsets = nullptr;
+  HJ_TRY(dev_alloc(c, &offsets, n + 1));
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
+                                                (DevStats*)nullptr, c->d_scalar)));
+  unsigned long long total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  if (total && (cs || wr)) {
+    const uint32_t nb = (uint32_t)((total + kUnnestTile - 1) / kUnnestTile);
+#define LAUNCH_UN(C, W) k_unnest<KeyT, C, W><<<nb, kUnnestThreads, 0, c->stream>>>(left, gref, n, offsets, groups, t->rows, out, cap, c->d_ctr)
+    if (cs) { if (wr) LAUNCH_UN(true, true); else LAUNCH_UN(true, false); }
+    else    { LAUNCH_UN(false, true); }
+#undef LAUNCH_UN
+    ++c->launches;
+  }
+  dev_free(c, offsets);
+  DevCounters* h = (DevCounters*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  res->matches = total; res->out_tuples = total; res->num_cmps = 0;     // AlgUnnestHt::_count = #outputs (algebra.hh:486-487)
+  res->checksum_sum = h->checksum_sum; res->checksum_xor = h->checksum_xor;
+  res->overflow = (wr && total > cap) ? 1 : 0;
+  res->out_written = wr ? (total > cap ? cap : total) : 0;
+  return HJ3D_OK;
+}
+
+int table_matches(hj3d_table* t, const hj3d_keyspec& ks) {
+  if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
+  if ((int)ks.hash_id != t->hash_id)
+    return fail(HJ3D_ERR_INVALID, "probe hash function differs from the build hash function "
+                                  "(static_assert in ht_chaining.hh:243 / ht_nested.hh:361)");
+  return HJ3D_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* hj3d_last_error(void) { return g_err.c_str(); }
+const char* hj3d_version(void) { return "hj3d 0.1 (sm_100a)"; }
+uint64_t hj3d_pair_mix(uint32_t l, uint32_t r) { return pair_mix(l, r); }
+
+int hj3d_ctx_create(int device, hj3d_ctx** out) {
+  if (!out) return fail(HJ3D_ERR_INVALID, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(HJ3D_ERR_CUDA, std::string("no CUDA device (this engine has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(HJ3D_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(HJ3D_ERR_CUDA, "hj3d kernels are built for sm_100a only; device is older");
+  CUDA_TRY(cudaSetDevice(device));
+  hj3d_ctx* c = new hj3d_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&c->pool, device));
+  uint64_t thr = UINT64_MAX;
+  CUDA_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  for (int i = 0; i < PH_COUNT; ++i) { CUDA_TRY(cudaEventCreate(&c->ev[i][0])); CUDA_TRY(cudaEventCreate(&c->ev[i][1])); c->ev_used[i] = false; }
+  CUDA_TRY(cudaEventCreate(&c->ev_total[0])); CUDA_TRY(cudaEventCreate(&c->ev_total[1]));
+  CUDA_TRY(cudaMalloc((void**)&c->d_ctr, sizeof(DevCounters)));
+  CUDA_TRY(cudaMalloc((void**)&c->d_stats, sizeof(DevStats)));
+  CUDA_TRY(cudaMalloc((void**)&c->d_scalar, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMallocHost(&c->h_pinned, 4096));
+  *out = c;
+  return HJ3D_OK;
+}
+
+int hj3d_ctx_destroy(hj3d_ctx* c) {
+  if (!c) return HJ3D_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < PH_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
+  cudaEventDestroy(c->ev_total[0]); cudaEventDestroy(c->ev_total[1]);
+  cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_scalar); cudaFreeHost(c->h_pinned);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return HJ3D_OK;
+}
+
+int hj3d_ctx_set_stream(hj3d_ctx* c, void* s) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "ctx == NULL");
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+  if (s) c->stream = (cudaStream_t)s;
+  else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  return HJ3D_OK;
+}
+
+int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "ctx == NULL");
+  switch (opt) {
+    case HJ3D_OPT_WARP_AGGREGATE:   c->warp_aggregate = v; break;
+    case HJ3D_OPT_PARTITION_BYTES:  c->partition_bytes = v; break;
+    case HJ3D_OPT_PARTITION_WINDOW: c->partition_window = v > 0 ? v : c->partition_window; break;
+    default: return fail(HJ3D_ERR_INVALID, "unknown option");
+  }
+  return HJ3D_OK;
+}
+
+int hj3d_ctx_sync(hj3d_ctx* c) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "ctx == NULL");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return HJ3D_OK;
+}
+
+int hj3d_ctx_timings(hj3d_ctx* c, hj3d_timings* out) {
+  if (!c || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float v[PH_COUNT];
+  for (int i = 0; i < PH_COUNT; ++i) {
+    v[i] = 0.f;
+    if (c->ev_used[i]) cudaEventElapsedTime(&v[i], c->ev[i][0], c->ev[i][1]);
+  }
+  out->partition_ms = v[PH_PARTITION]; out->histogram_ms = v[PH_HIST]; out->scan_ms = v[PH_SCAN];
+  out->scatter_ms = v[PH_SCATTER]; out->group_ms = v[PH_GROUP]; out->probe_ms = v[PH_PROBE]; out->unnest_ms = v[PH_UNNEST];
+  out->total_ms = 0.f;
+  cudaEventElapsedTime(&out->total_ms, c->ev_total[0], c->ev_total[1]);
+  cudaGetLastError();
+  out->kernel_launches = c->launches;
+  return HJ3D_OK;
+}
+
+int hj3d_owner_range(uint64_t D, uint32_t n_owners, uint32_t owner, uint64_t* lo, uint64_t* hi) {
+  if (!D || !n_owners || owner >= n_owners || !lo || !hi) return fail(HJ3D_ERR_INVALID, "bad owner range arguments");
+  const uint64_t w = (D + n_owners - 1) / n_owners;
+  *lo = (uint64_t)owner * w < D ? (uint64_t)owner * w : D;
+  *hi = (uint64_t)(owner + 1) * w < D ? (uint64_t)(owner + 1) * w : D;
+  return HJ3D_OK;
+}
+
+int hj3d_table_create_shard(hj3d_ctx* c, int kind, uint64_t D, uint64_t lo, uint64_t hi, hj3d_table** out) {
+  if (!c || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (kind != HJ3D_CHAINING && kind != HJ3D_NESTED) return fail(HJ3D_ERR_INVALID, "unknown table kind");
+  if (D == 0) return fail(HJ3D_ERR_INVALID, "num_buckets must be >= 1 (h % 0 is undefined in the reference too)");
+  if (D > 0xFFFFFFFFull) return fail(HJ3D_ERR_UNSUPPORTED, "num_buckets > 2^32-1 (the reference drivers use uint32_t, main_experiment1.cc:651)");
+  if (lo > hi || hi > D) return fail(HJ3D_ERR_INVALID, "bad bucket range");
+  hj3d_table* t = new hj3d_table();
+  t->kind = kind; t->D = D; t->blo = lo; t->bhi = hi;
+  t->dir = make_dir(D, lo, hi);
+  *out = t;
+  return HJ3D_OK;
+}
+
+int hj3d_table_create(hj3d_ctx* c, int kind, uint64_t D, hj3d_table** out) {
+  return hj3d_table_create_shard(c, kind, D, 0, D, out);
+}
+
+int hj3d_table_build(hj3d_ctx* c, hj3d_table* t, const void* d_tuples, uint64_t n, hj3d_keyspec ks) {
+  if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->built) return fail(HJ3D_ERR_INVALID, "table is not empty: call hj3d_table_clear first (bulk build)");
+  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
+  if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 build tuples (row ids are 32 bit; reference cap is 2^30, main_experiment1.cc:1391)");
+  HJ_TRY(check_keyspec(ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  begin_call(c);
+  Src src = make_src(d_tuples, n, ks, nullptr);
+  t->hash_id = (int)ks.hash_id; t->key_bytes = ks.key_bytes;
+  int rc;
+  switch (ks.hash_id) {
+    case HJ3D_HASH_MURMUR32: rc = build_impl<HJ3D_HASH_MURMUR32>(c, t, src); break;
+    case HJ3D_HASH_MURMUR64: rc = build_impl<HJ3D_HASH_MURMUR64>(c, t, src); break;
+    default:                 rc = build_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src); break;
+  }
+  end_call(c);
+  if (rc < 0) { free_table_arrays(c, t); return rc; }
+  return HJ3D_OK;
+}
+
+int hj3d_table_clear(hj3d_ctx* c, hj3d_table* t) {
+  if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  free_table_arrays(c, t);
+  return HJ3D_OK;
+}
+
+int hj3d_table_destroy(hj3d_ctx* c, hj3d_table* t) {
+  if (!t) return HJ3D_OK;
+  if (c) free_table_arrays(c, t);
+  delete t;
+  return HJ3D_OK;
+}
+
+int hj3d_table_size(hj3d_table* t, uint64_t* n, uint64_t* g) {
+  if (!t) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (n) *n = t->n;
+  if (g) *g = t->n_groups;
+  return HJ3D_OK;
+}
+
+int hj3d_table_stats(hj3d_ctx* c, hj3d_table* t, hj3d_stats* s) {
+  if (!c || !t || !s) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  memset(s, 0, sizeof(*s));
+  const uint64_t nl = t->dir.n_local;
+  s->num_buckets = nl;
+  if (!t->built) {   // an empty table: every bucket is empty (makeStatistics on a cleared table)
+    s->num_empty = nl; s->cc_min = nl ? 0 : ~0ull; s->cc_count = nl; s->ccne_min = ~0ull;
+    s->mem_dir = nl * (t->kind == HJ3D_CHAINING ? 24 : 32);
+    return HJ3D_OK;
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const DevStats& h = t->hstats;
+  s->num_empty = h.empty; s->num_entries = t->n;
+  s->cc_min = h.all.mn; s->cc_max = h.all.mx; s->cc_sum = h.all.sum; s->cc_sumsq = h.all.sumsq; s->cc_count = h.all.cnt;
+  s->ccne_min = h.nonempty.mn; s->ccne_max = h.nonempty.mx; s->ccne_sum = h.nonempty.sum;
+  s->ccne_sumsq = h.nonempty.sumsq; s->ccne_count = h.nonempty.cnt;
+  const uint64_t nonempty = nl - h.empty;
+  if (t->kind == HJ3D_CHAINING) {
+    // distinct low-32 hash bits via a 2^32-bit bitmap (only here, outside any timed path; the
+    // reference's makeStatistics is likewise called after the timed region, main_experiment1.cc:710)
+    uint32_t* bitmap = nullptr;
+    const uint64_t words = 1ull << 27;
+    HJ_TRY(dev_alloc(c, &bitmap, words));
+    CUDA_TRY(cudaMemsetAsync(bitmap, 0, words * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 8, c->stream));
+    if (t->n) {
+      const uint32_t nb = blocks_for(t->n, 256);
+      switch (t->hash_id) {
+        case HJ3D_HASH_MURMUR32: k_hash_bitmap<HJ3D_HASH_MURMUR32><<<nb, 256, 0, c->stream>>>((const Slot<uint32_t>*)t->slots, t->n, bitmap); break;
+        case HJ3D_HASH_MURMUR64: k_hash_bitmap<HJ3D_HASH_MURMUR64><<<nb, 256, 0, c->stream>>>((const Slot<uint64_t>*)t->slots, t->n, bitmap); break;
+        default: k_hash_bitmap<HJ3D_HASH_MURMUR64_SEXT32><<<nb, 256, 0, c->stream>>>((const Slot<uint32_t>*)t->slots, t->n, bitmap); break;
+      }
+      k_popcount<<<c->sm_count * 8, 256, 0, c->stream>>>(bitmap, words, c->d_scalar);
+      c->launches += 2;
+    }
+    unsigned long long dk = 0;
+    CUDA_TRY(cudaMemcpyAsync(&dk, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+    dev_free(c, bitmap);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->num_distinct_keys = dk;
+    s->rsv_main = t->n - nonempty;                       // every tuple but the first of a bucket takes a reservoir node
+    s->rsv_sub = 0;
+    s->mem_dir = nl * 24; s->mem_main = s->rsv_main * 24; s->mem_sub = 0;
+  } else {
+    s->num_distinct_keys = t->n_groups;                  // Sum of main chain lengths (ht_nested.hh:470)
+    s->rsv_main = t->n_groups - nonempty;
+    s->rsv_sub = t->n - t->n_groups;
+    s->mem_dir = nl * 32; s->mem_main = s->rsv_main * 32; s->mem_sub = s->rsv_sub * 16;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+int hj3d_stats_merge(const hj3d_stats* p, uint32_t n, hj3d_stats* o) {
+  if (!p || !o || !n) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  memset(o, 0, sizeof(*o));
+  o->cc_min = ~0ull; o->ccne_min = ~0ull;
+  for (uint32_t i = 0; i < n; ++i) {
+    const hj3d_stats& s = p[i];
+    o->num_buckets += s.num_buckets; o->num_empty += s.num_empty; o->num_entries += s.num_entries;
+    o->num_distinct_keys += s.num_distinct_keys;   // exact for nested; for chaining exact when the hash is injective on 32 bits
+    if (s.cc_count)   { o->cc_min = s.cc_min < o->cc_min ? s.cc_min : o->cc_min; o->cc_max = s.cc_max > o->cc_max ? s.cc_max : o->cc_max; }
+    if (s.ccne_count) { o->ccne_min = s.ccne_min < o->ccne_min ? s.ccne_min : o->ccne_min; o->ccne_max = s.ccne_max > o->ccne_max ? s.ccne_max : o->ccne_max; }
+    o->cc_sum += s.cc_sum; o->cc_sumsq += s.cc_sumsq; o->cc_count += s.cc_count;
+    o->ccne_sum += s.ccne_sum; o->ccne_sumsq += s.ccne_sumsq; o->ccne_count += s.ccne_count;
+    o->rsv_main += s.rsv_main; o->rsv_sub += s.rsv_sub;
+    o->mem_dir += s.mem_dir; o->mem_main += s.mem_main; o->mem_sub += s.mem_sub;
+  }
+  return HJ3D_OK;
+}
+
+int hj3d_probe_chaining(hj3d_ctx* c, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks,
+                        const uint32_t* d_gather, int unique, uint32_t flags,
+                        uint32_t* d_out, uint64_t cap, hj3d_counters* out) {
+  if (!c || !t || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_CHAINING) return fail(HJ3D_ERR_INVALID, "hj3d_probe_chaining needs a chaining table");
+  if (n && !d_probe) return fail(HJ3D_ERR_INVALID, "d_probe == NULL");
+  if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 probe tuples");
+  HJ_TRY(check_keyspec(ks));
+  HJ_TRY(table_matches(t, ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  Src src = make_src(d_probe, n, ks, d_gather);
+  int rc;
+  {
+    PhaseTimer pt(c, PH_PROBE);
+    switch (ks.hash_id) {
+      case HJ3D_HASH_MURMUR32: rc = probe_chaining_impl<HJ3D_HASH_MURMUR32>(c, t, src, unique != 0, flags, (uint2*)d_out, cap); break;
+      case HJ3D_HASH_MURMUR64: rc = probe_chaining_impl<HJ3D_HASH_MURMUR64>(c, t, src, unique != 0, flags, (uint2*)d_out, cap); break;
+      default:                 rc = probe_chaining_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src, unique != 0, flags, (uint2*)d_out, cap); break;
+    }
+  }
+  end_call(c);
+  if (rc < 0) return rc;
+  HJ_TRY(fetch_counters(c, out, cap, d_out != nullptr));
+  return out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_probe_nested(hj3d_ctx* c, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks,
+                      const uint32_t* d_gather, uint32_t flags, uint32_t* d_out, uint64_t cap, hj3d_counters* out) {
+  if (!c || !t || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_NESTED) return fail(HJ3D_ERR_INVALID, "hj3d_probe_nested needs a nested table");
+  if (n && !d_probe) return fail(HJ3D_ERR_INVALID, "d_probe == NULL");
+  if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 probe tuples");
+  HJ_TRY(check_keyspec(ks));
+  HJ_TRY(table_matches(t, ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  Src src = make_src(d_probe, n, ks, d_gather);
+  int rc;
+  {
+    PhaseTimer pt(c, PH_PROBE);
+    switch (ks.hash_id) {
+      case HJ3D_HASH_MURMUR32: rc = probe_nested_impl<HJ3D_HASH_MURMUR32>(c, t, src, flags, (uint2*)d_out, cap); break;
+      case HJ3D_HASH_MURMUR64: rc = probe_nested_impl<HJ3D_HASH_MURMUR64>(c, t, src, flags, (uint2*)d_out, cap); break;
+      default:                 rc = probe_nested_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src, flags, (uint2*)d_out, cap); break;
+    }
+  }
+  end_call(c);
+  if (rc < 0) return rc;
+  HJ_TRY(fetch_counters(c, out, cap, d_out != nullptr));
+  return out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_unnest(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_left, const uint32_t* d_gref, uint64_t n,
+                uint32_t flags, uint32_t* d_out, uint64_t cap, hj3d_counters* out) {
+  if (!c || !t || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_NESTED) return fail(HJ3D_ERR_INVALID, "hj3d_unnest needs a nested table");
+  if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
+  if (n && (!d_left || !d_gref)) return fail(HJ3D_ERR_INVALID, "NULL input column");
+  CUDA_TRY(cudaSetDevice(c->device));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  memset(out, 0, sizeof(*out));
+  int rc;
+  {
+    PhaseTimer pt(c, PH_UNNEST);
+    if (t->key_bytes == 8) rc = unnest_impl<uint64_t>(c, t, d_left, d_gref, n, flags, (uint2*)d_out, cap, out);
+    else                   rc = unnest_impl<uint32_t>(c, t, d_left, d_gref, n, flags, (uint2*)d_out, cap, out);
+  }
+  end_call(c);
+  if (rc < 0) return rc;
+  return out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_group_first_row(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_gref, uint64_t n, uint32_t* d_out) {
+  if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_NESTED || !t->built) return fail(HJ3D_ERR_INVALID, "needs a built nested table");
+  if (!n) return HJ3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (t->key_bytes == 8) k_group_first_row<uint64_t><<<blocks_for(n, 256), 256, 0, c->stream>>>((const Group<uint64_t>*)t->groups, d_gref, n, d_out);
+  else                   k_group_first_row<uint32_t><<<blocks_for(n, 256), 256, 0, c->stream>>>((const Group<uint32_t>*)t->groups, d_gref, n, d_out);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+int hj3d_gather_u32(hj3d_ctx* c, const uint32_t* d_src, const uint32_t* d_idx, uint64_t n, uint32_t* d_dst) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!n) return HJ3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  k_gather_u32<<<blocks_for(n, 256), 256, 0, c->stream>>>(d_src, d_idx, n, d_dst);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+int hj3d_split_pairs(hj3d_ctx* c, const uint32_t* d_pairs, uint64_t n, uint32_t* d_left, uint32_t* d_right) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!n) return HJ3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  k_split_pairs<<<blocks_for(n, 256), 256, 0, c->stream>>>((const uint2*)d_pairs, n, d_left, d_right);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+int hj3d_join_host(hj3d_ctx* c, int mode,
+                   const void* h_build, uint64_t nB, hj3d_keyspec ksB, uint64_t D,
+                   const void* h_probe, uint64_t nP, hj3d_keyspec ksP, uint32_t flags,
+                   uint32_t* h_out, uint64_t cap, hj3d_counters* pc, hj3d_counters* uc, hj3d_stats* st) {
+  if (!c || !pc) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (mode < 0 || mode > 3) return fail(HJ3D_ERR_INVALID, "mode must be 0..3");
+  if (mode == 3 && !uc) return fail(HJ3D_ERR_INVALID, "unnest_out == NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  void *dB = nullptr, *dP = nullptr; uint32_t *dOut = nullptr, *dNest = nullptr, *dL = nullptr, *dG = nullptr;
+  hj3d_table* t = nullptr;
+  int rc = HJ3D_OK;
+  auto cleanup = [&]() {
+    dev_free(c, dB); dev_free(c, dP); dev_free(c, dOut); dev_free(c, dNest); dev_free(c, dL); dev_free(c, dG);
+    if (t) hj3d_table_destroy(c, t);
+  };
+#define JH_TRY(expr) do { rc = (expr); if (rc < 0) { cleanup(); return rc; } } while (0)
+  uint8_t* b8 = nullptr; uint8_t* p8 = nullptr;
+  JH_TRY(dev_alloc(c, &b8, nB * ksB.tuple_bytes)); dB = b8;
+  JH_TRY(dev_alloc(c, &p8, nP * ksP.tuple_bytes)); dP = p8;
+  if (nB) { cudaError_t e = cudaMemcpyAsync(dB, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); } }
+  if (nP) { cudaError_t e = cudaMemcpyAsync(dP, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); } }
+  JH_TRY(hj3d_table_create(c, mode <= 1 ? HJ3D_CHAINING : HJ3D_NESTED, D, &t));
+  JH_TRY(hj3d_table_build(c, t, dB, nB, ksB));
+  const bool want_pairs = h_out != nullptr || (flags & HJ3D_F_DEVICE_RESULT);
+  int final_rc = HJ3D_OK;
+  uint64_t n_out = 0;
+  if (mode <= 1) {
+    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
+    JH_TRY(hj3d_probe_chaining(c, t, dP, nP, ksP, nullptr, mode == 1, flags, dOut, cap, pc));
+    final_rc = rc; n_out = pc->out_written;
+  } else if (mode == 2) {
+    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
+    JH_TRY(hj3d_probe_nested(c, t, dP, nP, ksP, nullptr, flags, dOut, cap, pc));
+    final_rc = rc; n_out = pc->out_written;
+  } else {
+    JH_TRY(dev_alloc(c, &dNest, nP * 2));
+    JH_TRY(hj3d_probe_nested(c, t, dP, nP, ksP, nullptr, flags, dNest, nP, pc));
+    const uint64_t m = pc->out_written;
+    JH_TRY(dev_alloc(c, &dL, m)); JH_TRY(dev_alloc(c, &dG, m));
+    JH_TRY(hj3d_split_pairs(c, dNest, m, dL, dG));
+    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
+    JH_TRY(hj3d_unnest(c, t, dL, dG, m, flags, dOut, cap, uc));
+    final_rc = rc; n_out = uc->out_written;
+  }
+  if (h_out && n_out) {
+    cudaError_t e = cudaMemcpyAsync(h_out, dOut, n_out * 8, cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  if (st) JH_TRY(hj3d_table_stats(c, t, st));
+  cudaStreamSynchronize(c->stream);
+  cleanup();
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e));
+#undef JH_TRY
+  return final_rc;
+}
+
+int hj3d_partition_by_owner(hj3d_ctx* c, const void* d_tuples, uint64_t n, hj3d_keyspec ks,
+                            uint64_t D, uint32_t n_owners, uint32_t rowid_base, void* d_out, uint64_t* h_counts) {
+  if (!c || !h_counts) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!D || D > 0xFFFFFFFFull || !n_owners || n_owners > 1024) return fail(HJ3D_ERR_INVALID, "bad num_buckets / n_owners");
+  if (n && (!d_tuples || !d_out)) return fail(HJ3D_ERR_INVALID, "NULL buffer");
+  HJ_TRY(check_keyspec(ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  begin_call(c);
+  int rc;
+  {
+    PhaseTimer pt(c, PH_PARTITION);
+    Src src = make_src(d_tuples, n, ks, nullptr);
+    Dir d = make_dir(D, 0, D);
+    const uint32_t width = (uint32_t)((D + n_owners - 1) / n_owners);
+    unsigned long long* d_counts = nullptr;
+    rc = dev_alloc(c, &d_counts, 2ull * n_owners);
+    if (rc == HJ3D_OK) {
+      cudaMemsetAsync(d_counts, 0, 2ull * n_owners * 8, c->stream);
+      switch (ks.hash_id) {
+        case HJ3D_HASH_MURMUR32: rc = partition_by_owner_impl<HJ3D_HASH_MURMUR32>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
+        case HJ3D_HASH_MURMUR64: rc = partition_by_owner_impl<HJ3D_HASH_MURMUR64>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
+        default:                 rc = partition_by_owner_impl<HJ3D_HASH_MURMUR64_SEXT32>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
+      }
+      std::vector<unsigned long long> hc(n_owners);
+      cudaMemcpyAsync(hc.data(), d_counts, n_owners * 8ull, cudaMemcpyDeviceToHost, c->stream);
+      cudaStreamSynchronize(c->stream);
+      for (uint32_t i = 0; i < n_owners; ++i) h_counts[i] = hc[i];
+      dev_free(c, d_counts);
+    }
+  }
+  end_call(c);
+  if (rc < 0) return fail(rc, "partition_by_owner failed");
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+}  // extern "C"

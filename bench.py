@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: join input tuples/s (build + probe) of the key/foreign-key join of
+main_experiment1 at the reference's largest shape (-R 27 -S 30: 2^27 build / 2^30 probe, uint32 keys,
+12-byte {k,a,b} row-store tuples, b=1 => 2^27 buckets), plan Csr (chaining, IsBuildKeyUnique) with
+materialised (probe row, build row) result pairs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--plan Csr|CsrUU|Nsr|Crs|Nrs]
+                    [--log2-build 27 --log2-probe 30]
+
+One "step" = clear the table, build strand, probe strand (+ unnest for nested plans) over one batch of
+synthetic input resident in HBM.  N > 1 (torchrun): the same total workload is sharded by bucket range
+(strong scaling): every rank partitions its slice of both relations by owner, exchanges (key, global row
+id) records with an NCCL all-to-all, and joins its shard locally; partition + exchange are inside the
+timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PLANS = {  # plan -> (table kind, build relation, mode)   mode: 1 chaining unique, 0 chaining, 3 nested+unnest
+    "Csr": ("chaining", "R", 1), "CsrUU": ("chaining", "R", 0), "Nsr": ("nested", "R", 3),
+    "Crs": ("chaining", "S", 0), "Nrs": ("nested", "S", 3),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(float(s[0])) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def algorithmic_bytes(nB, nP, nM, nO, D, T=12, K=4, I=4, nested=False):
+    """compulsory + table traffic of one join, design independent."""
+    out = nO * 2 * I + (nM * 2 * I * 2 if nested else 0)
+    compulsory = nB * T + nP * T + out
+    table = nB * (K + I) + D * 4 + nP * (4 + K + I)
+    return compulsory + table
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref, the unmodified templates; else the C port) on a
+    bounded sample of the same workload shape: build 2^sb / probe 2^(sb+3), single thread (the reference has
+    no parallel path)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    kind_name, build_rel, mode = PLANS[args.plan]
+    sb = args.ref_log2_build
+    nR, nS = 1 << sb, 1 << (sb + (args.log2_probe - args.log2_build))
+    rng = np.random.default_rng(1)
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR).astype(np.uint32)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS, dtype=np.uint32); S[:, 1] = rng.integers(0, nR, nS, dtype=np.uint32)
+    use_ref = pyoracle.Ref.available()
+    impl = pyoracle.Ref() if use_ref else pyoracle.Oracle()
+    ksR, ksS = pyoracle.KeySpec(12, 0), pyoracle.KeySpec(12, 4)
+    B, ksB, P, ksP = (R, ksR, S, ksS) if build_rel == "R" else (S, ksS, R, ksR)
+    D = nR if build_rel == "R" else max(len(np.unique(S[:, 1])), 1)
+    kind = pyoracle.CHAINING if kind_name == "chaining" else pyoracle.NESTED
+    times = []
+    for it in range(args.warmup + args.steps):
+        if use_ref:
+            t = impl.build(kind, B, len(B), ksB, D, timed=True)
+            c, cu, _, ns = t.probe(P, len(P), ksP, mode, timing_top=True)
+            dt = (t.build_ns + ns) * 1e-9
+        else:
+            t0 = time.perf_counter()
+            t = impl.build(kind, B, len(B), ksB, D)
+            if mode <= 1:
+                t.probe_chaining(P, len(P), ksP, unique=(mode == 1), materialize=False)
+            else:
+                c, nest = t.probe_nested(P, len(P), ksP)
+                t.unnest(nest[:, 0], nest[:, 1])
+            dt = time.perf_counter() - t0
+        del t
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = (nR + nS) / (ms * 1e-3)
+    sample = f"plan {args.plan}, build 2^{sb} / probe 2^{sb + (args.log2_probe - args.log2_build)} of the same generator, 1 thread"
+    line = {"impl": "reference", "metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": "tuples/s", "cores": 1, "kind": "reference" if use_ref else "port",
+                             "sample": sample, "host_cores": os.cpu_count()},
+            "e2e": {"value": value, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"main_experiment1 key/foreign-key join -R {args.log2_build} -S {args.log2_probe} --no-skew -t 0 -b 1, "
+                        f"plan {args.plan}, uint32 keys, 12-byte row-store tuples, materialised result pairs",
+            "plan": args.plan, "log2_build": args.log2_build, "log2_probe": args.log2_probe,
+            "l2_policy": "inputs (>= 1.6 GB + 12.9 GB) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"bucket-range sharding over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def cpu_baseline_leg(args):
+    """Bounded sample of the same workload on the box's host cores (rank 0, N=1 only)."""
+    try:
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        kind_name, build_rel, mode = PLANS[args.plan]
+        sb = args.ref_log2_build
+        nR, nS = 1 << sb, 1 << (sb + (args.log2_probe - args.log2_build))
+        rng = np.random.default_rng(1)
+        R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR).astype(np.uint32)
+        S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS, dtype=np.uint32); S[:, 1] = rng.integers(0, nR, nS, dtype=np.uint32)
+        ksR, ksS = pyoracle.KeySpec(12, 0), pyoracle.KeySpec(12, 4)
+        B, ksB, P, ksP = (R, ksR, S, ksS) if build_rel == "R" else (S, ksS, R, ksR)
+        D = nR if build_rel == "R" else max(len(np.unique(S[:, 1])), 1)
+        kind = pyoracle.CHAINING if kind_name == "chaining" else pyoracle.NESTED
+        if pyoracle.Ref.available():
+            ref = pyoracle.Ref()
+            t = ref.build(kind, B, len(B), ksB, D, timed=True)
+            c, cu, _, ns = t.probe(P, len(P), ksP, mode, timing_top=True)
+            dt, k = (t.build_ns + ns) * 1e-9, "reference"
+        else:
+            orc = pyoracle.Oracle()
+            t0 = time.perf_counter()
+            t = orc.build(kind, B, len(B), ksB, D)
+            t.probe_chaining(P, len(P), ksP, unique=(mode == 1), materialize=False)
+            dt, k = time.perf_counter() - t0, "port"
+        return {"value": (nR + nS) / dt, "unit": "tuples/s", "cores": 1, "kind": k, "host_cores": os.cpu_count(),
+                "sample": f"plan {args.plan}, build 2^{sb} / probe 2^{sb + (args.log2_probe - args.log2_build)}, 1 repetition, 1 thread "
+                          "(the reference is single-threaded)", "seconds": dt}
+    except Exception as e:  # the baseline is a reported side figure; never fail the bench for it
+        return {"value": None, "unit": "tuples/s", "cores": 1, "kind": "unavailable", "sample": repr(e)}
+
+
+def run_ours(args):
+    import torch
+    import hj3d_loader
+    pkg = hj3d_loader.load()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = pkg.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    kind_name, build_rel, mode = PLANS[args.plan]
+    kind = pkg.CHAINING if kind_name == "chaining" else pkg.NESTED
+    nR, nS = 1 << args.log2_build, 1 << args.log2_probe
+    # ---- synthetic relations, generated on the device (rank r holds rows [r*n/N, (r+1)*n/N) of both)
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    if world == 1:
+        Rk = torch.randperm(nR, device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+    else:  # a bijection of [0, nR) that every rank can evaluate on its own slice: k -> (a*k + c) mod nR, a odd
+        lo = rank * (nR // world)
+        idx = torch.arange(lo, lo + nR // world, device=dev, dtype=torch.int64)
+        Rk = ((idx * 0x9E3779B1 + 12345) % nR).to(torch.int32)
+    nRl, nSl = nR // world, nS // world
+    R = torch.zeros((nRl, 3), dtype=torch.int32, device=dev); R[:, 0] = Rk; del Rk
+    g.manual_seed(99 + rank)
+    S = torch.zeros((nSl, 3), dtype=torch.int32, device=dev)
+    S[:, 0] = torch.arange(rank * nSl, (rank + 1) * nSl, device=dev, dtype=torch.int64).to(torch.int32)
+    S[:, 1] = torch.randint(0, nR, (nSl,), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+    ksRk, ksSa = pkg.KeySpec(12, 0), pkg.KeySpec(12, 4)
+    B, ksB, nBl, P, ksP, nPl = (R, ksRk, nRl, S, ksSa, nSl) if build_rel == "R" else (S, ksSa, nSl, R, ksRk, nRl)
+    nBg, nPg = (nR, nS) if build_rel == "R" else (nS, nR)
+    if build_rel == "R":
+        D = nR
+    else:
+        D = nR - int(nR * (1 - 1 / nR) ** nS) if nR > 1 else 1     # ~ #distinct S.a (numDvSa); any D is a valid table size
+    ks_rec = pkg.KeySpec(8, 0, 4, 0, 4)
+    lib = pkg.capi.load()
+    if world > 1:
+        lo_, hi_ = C.c_uint64(), C.c_uint64()
+        lib.hj3d_owner_range(D, world, rank, C.byref(lo_), C.byref(hi_))
+        table = ctx.table(kind, D, shard=(lo_.value, hi_.value))
+    else:
+        table = ctx.table(kind, D)
+    cap_out = int(nS // world * 1.25) + 1024 if world > 1 else nS
+    out = torch.empty((cap_out, 2), dtype=torch.int32, device=dev)
+    nest = torch.empty((max(nPl * (2 if world > 1 else 1), 1), 2), dtype=torch.int32, device=dev) if mode == 3 else None
+    part_B = torch.empty((nBl, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    part_P = torch.empty((nPl, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    flags = pkg.F_CHECKSUM if args.checksum else 0
+    state = {}
+
+    def exchange(src, n, ks, part, base):
+        counts = ctx.partition_by_owner(src, n, ks, D, world, base, part)
+        sc = torch.tensor(counts, dtype=torch.int64, device=dev)
+        rc_ = torch.empty_like(sc)
+        dist.all_to_all_single(rc_, sc)
+        rcounts = rc_.tolist()
+        recv = torch.empty((sum(rcounts), 2), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(recv, part, output_split_sizes=rcounts, input_split_sizes=counts)
+        state["shuffle_bytes"] = state.get("shuffle_bytes", 0) + 8 * (n - counts[rank])
+        return recv, recv.shape[0]
+
+    def step():
+        state["shuffle_bytes"] = 0
+        table.clear()
+        if world > 1:
+            bsrc, nb = exchange(B, nBl, ksB, part_B, rank * nBl)
+            psrc, npb = exchange(P, nPl, ksP, part_P, rank * nPl)
+            kb, kp = ks_rec, ks_rec
+        else:
+            bsrc, nb, psrc, npb, kb, kp = B, nBl, P, nPl, ksB, ksP
+        table.build(bsrc, nb, kb)
+        tb = ctx.timings()
+        if mode <= 1:
+            rc, c = table.probe_chaining(psrc, npb, kp, unique=(mode == 1), flags=flags, out=out, out_cap=cap_out)
+            tp = ctx.timings()
+            res = c
+        else:
+            rc, c = table.probe_nested(psrc, npb, kp, flags=flags, out=nest, out_cap=nest.shape[0])
+            tp = ctx.timings()
+            m = c["out_written"]
+            left, gref = nest[:m, 0].contiguous(), nest[:m, 1].contiguous()
+            rc, res = table.unnest(left, gref, m, flags=flags, out=out, out_cap=cap_out)
+            state["unnest_ms"] = ctx.timings()["unnest_ms"]
+        assert rc == 0, "result buffer overflow"
+        state.update(build=tb, probe=tp, probe_counters=c, result=res, n_probe_local=npb)
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ctx.timings()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    probe_ms, build_ms = [], []
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+        probe_ms.append(state["probe"]["probe_ms"]); build_ms.append(state["build"]["total_ms"])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ctx.timings()["kernel_launches"] - launches0
+    clocks = sampler.summary() if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tot = torch.tensor([res["out_tuples"], state["probe_counters"]["num_cmps"], launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        out_total, cmps_total, launches = [int(x) for x in tot.tolist()]
+    else:
+        out_total, cmps_total = res["out_tuples"], state["probe_counters"]["num_cmps"]
+    # size-independent correctness properties at full size: every S tuple finds exactly one R partner
+    assert out_total == nS, f"join produced {out_total} tuples, expected |S| = {nS}"
+    value = (nR + nS) / (ms * 1e-3)
+    # ---- e2e: host buffers through hj3d_join_host (H2D of both relations + D2H of the counters inside)
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        try:
+            hB = torch.empty((nBl, 3), dtype=torch.int32).pin_memory(); hB.copy_(B)
+            hP = torch.empty((nPl, 3), dtype=torch.int32).pin_memory(); hP.copy_(P)
+            out_keep = out
+            del out
+            torch.cuda.empty_cache()
+            ts = []
+            for it in range(1 + args.e2e_steps):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                rc, pc, uc, _ = ctx.join_host(mode, hB, nBl, ksB, D, hP, nPl, ksP, flags=flags | 2, h_out=None, out_cap=nS)
+                torch.cuda.synchronize(); dt = time.perf_counter() - t0
+                if it:
+                    ts.append(dt)
+                assert (uc if mode == 3 else pc)["out_tuples"] == nS
+            e2e_s = sum(ts) / len(ts)
+            e2e = {"value": (nR + nS) / e2e_s, "unit": "tuples/s", "h2d_bytes_per_step": 12 * (nR + nS),
+                   "d2h_bytes_per_step": 56, "ms_per_step": e2e_s * 1e3, "steps": len(ts),
+                   "note": "pinned host relations -> hj3d_join_host -> counters on the host; result pairs materialised in HBM"}
+            del hB, hP
+        except Exception as ex:
+            e2e = {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 12 * (nR + nS), "d2h_bytes_per_step": 56,
+                   "error": repr(ex)}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = peaks()
+    nested = mode == 3
+    nM = state["probe_counters"]["matches"] if nested else 0
+    alg = algorithmic_bytes(nBg, nPg, nM * world if nested else 0, nS, D, nested=nested)
+    # dominant kernel: the probe kernel.  32 B per probe tuple: 12 B tuple + 4 B directory word + 8 B slot + 8 B result pair
+    pm = sum(probe_ms) / len(probe_ms)
+    probe_bytes = state["n_probe_local"] * (12 + 4 + 8 + 8)
+    line = {"metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e if e2e is not None else {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                               "note": "e2e is measured at N=1"},
+            "roofline": {"bound": "hbm", "kernel": "k_probe_chaining" if mode <= 1 else "k_probe_nested",
+                         "achieved": probe_bytes / (pm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": probe_bytes / (pm * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": pm, "algorithmic_bytes_per_launch": probe_bytes,
+                         "join_algorithmic_bytes": alg, "join_frac": alg / (ms * 1e-3) / 1e9 / peak / world},
+            "phases_ms": {"build_total": sum(build_ms) / len(build_ms), "histogram": state["build"]["histogram_ms"],
+                          "scan": state["build"]["scan_ms"], "scatter": state["build"]["scatter_ms"],
+                          "group": state["build"]["group_ms"], "probe": pm, "unnest": state.get("unnest_ms", 0.0)},
+            "result": {"out_tuples": out_total, "num_cmps": cmps_total, "checksum_sum": res["checksum_sum"] if world == 1 else None}}
+    if world > 1:
+        line["shuffle"] = {"bytes_sent_per_gpu": state["shuffle_bytes"], "note": "NCCL all_to_all_single of (key,row id) records"}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--plan", default="Csr", choices=list(PLANS))
+    ap.add_argument("--log2-build", type=int, default=27)
+    ap.add_argument("--log2-probe", type=int, default=30)
+    ap.add_argument("--ref-log2-build", type=int, default=22, help="sample size of the CPU reference legs")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-checksum", dest="checksum", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+/*
+ * hj3d.h -- C ABI of the B200-native 3D hash-join engine (libhj3d.so).
+ *
+ * The reference (dflaxx/3d-hashjoin) has no FFI: its boundary is the template
+ * protocol of algebra.hh.  This header is the device-side replacement of the
+ * hot path *below* that protocol; the C++20 operator templates in
+ * 3d-hashjoin_b200/hostcpp/hj3d/ (same names and constructor signatures as
+ * algebra.hh) are thin shims over it.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - pointers named d_* are device pointers (cudaMalloc / torch storage on the ctx's device),
+ *     h_* are host pointers, everything else (counters, stats, handles) lives on the host
+ *   - return value 0 = HJ3D_OK, < 0 = error (hj3d_last_error() has the text),
+ *     HJ3D_OVERFLOW (1) = result capacity too small: counters are exact, pairs beyond
+ *     out_cap were dropped
+ *   - one CUDA stream per ctx; a ctx and its tables are not thread safe (neither is the reference)
+ *   - there is NO CPU fallback: every call fails with HJ3D_ERR_CUDA when no sm_100 device is usable
+ */
+#ifndef HJ3D_H
+#define HJ3D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HJ3D_OK               0
+#define HJ3D_OVERFLOW         1
+#define HJ3D_ERR_INVALID     -1
+#define HJ3D_ERR_CUDA        -2
+#define HJ3D_ERR_UNSUPPORTED -3
+#define HJ3D_ERR_NOMEM       -4
+
+/* table kinds: ht_chaining.hh:38-158 (HtChaining1) / ht_nested.hh:71-251 (HtNested1) */
+#define HJ3D_CHAINING 0
+#define HJ3D_NESTED   1
+
+/* hash functions (util/hasht.hh:52-72) as used by the drivers' Hashfun* functors */
+#define HJ3D_HASH_MURMUR32        0 /* uint32 key -> ht::murmur_hash<uint32_t>   (main_experiment1.cc:231,288-301) */
+#define HJ3D_HASH_MURMUR64        1 /* uint64 key -> ht::murmur_hash<uint64_t>   (tuple_types.hh:13,17)            */
+#define HJ3D_HASH_MURMUR64_SEXT32 2 /* int32 key, sign extended -> murmur_hash<uint64_t> (main_algebra_example.cc:48-66) */
+
+#define HJ3D_NO_ROWID 0xFFFFFFFFu
+
+/* probe / unnest flags */
+#define HJ3D_F_CHECKSUM      1u /* also fold every result pair into checksum_sum / checksum_xor */
+#define HJ3D_F_DEVICE_RESULT 2u /* hj3d_join_host: materialise the result pairs in device memory even when
+                                 h_out_pairs is NULL (they are not copied back) */
+
+/* ctx options (hj3d_ctx_set_option) */
+#define HJ3D_OPT_WARP_AGGREGATE   1 /* 0/1: warp-aggregate equal buckets before atomics (default 1)            */
+#define HJ3D_OPT_PARTITION_BYTES  2 /* table bytes above which inputs are bucket-range partitioned first;
+                                       0 = never partition (default: 48 MiB)                                   */
+#define HJ3D_OPT_PARTITION_WINDOW 3 /* target table-window bytes per partition (default 16 MiB)                */
+
+/*
+ * Device-describable form of the drivers' hash / equality functors (concepts.hh:22-28,49-56):
+ * the join attribute is the key_bytes wide integer at key_offset of each tuple_bytes wide
+ * row-store tuple (RelationRS, algebra.hh:98-106); it is hashed with hash_id and compared for
+ * equality.  rowid_offset != HJ3D_NO_ROWID: the tuple carries its own uint32 row id (used after
+ * the multi-GPU exchange, where tuples are (key, global row id) pairs).
+ */
+typedef struct {
+  uint32_t tuple_bytes;
+  uint32_t key_offset;
+  uint32_t key_bytes;
+  uint32_t hash_id;
+  uint32_t rowid_offset;
+} hj3d_keyspec;
+
+/* What the probe-side operators expose: AlgBase::count() (algebra.hh:178) and numCmps()
+ * (algebra.hh:467,666), plus an order-independent checksum of the result multiset. */
+typedef struct {
+  uint64_t matches;      /* AlgHashJoinProbe / AlgNestJoinProbe / AlgUnnestHt ::count()          */
+  uint64_t num_cmps;     /* ::numCmps()                                                          */
+  uint64_t out_tuples;   /* result tuples produced (what AlgTop::count() sees, algebra.hh:223-229) */
+  uint64_t checksum_sum; /* sum and xor over hj3d_pair_mix(left, right) of every result pair     */
+  uint64_t checksum_xor;
+  uint64_t out_written;  /* pairs actually stored to d_out_pairs                                 */
+  uint64_t overflow;     /* 1 if out_tuples > out_cap                                            */
+} hj3d_counters;
+
+/* HtStatistics (ht_statistics.hh:18-54) as filled by makeStatistics (ht_chaining.hh:260-292,
+ * ht_nested.hh:450-482), plus the reservoir / memory getters (ht_chaining.hh:113-117,161-177;
+ * ht_nested.hh:192-198,262-284).  Aggregate<size_t> (util/aggregate.hh:27-68) is flattened to
+ * min,max,sum,sumsq,count. */
+typedef struct {
+  uint64_t num_buckets, num_empty, num_entries, num_distinct_keys;
+  uint64_t cc_min, cc_max, cc_sum, cc_sumsq, cc_count;           /* _collisionChainLen         */
+  uint64_t ccne_min, ccne_max, ccne_sum, ccne_sumsq, ccne_count; /* _collisionChainLenNonempty */
+  uint64_t rsv_main, rsv_sub;        /* getRsvSize() | getRsvMainSize(), getRsvSubSize()       */
+  uint64_t mem_dir, mem_main, mem_sub; /* memoryConsupmtionDir / Chains | MainChains / SubChains */
+} hj3d_stats;
+
+/* per-phase device times of the last call on the ctx (CUDA events on the ctx's stream), ms */
+typedef struct {
+  float partition_ms, histogram_ms, scan_ms, scatter_ms, group_ms, probe_ms, unnest_ms, total_ms;
+  uint64_t kernel_launches; /* kernels launched by the engine since ctx creation */
+} hj3d_timings;
+
+typedef struct hj3d_ctx   hj3d_ctx;
+typedef struct hj3d_table hj3d_table;
+
+const char* hj3d_last_error(void);
+const char* hj3d_version(void);
+/* checksum contribution of one (left,right) pair; host helper so callers / tests use one definition */
+uint64_t    hj3d_pair_mix(uint32_t left, uint32_t right);
+
+int hj3d_ctx_create(int device, hj3d_ctx** out);
+int hj3d_ctx_destroy(hj3d_ctx* ctx);
+int hj3d_ctx_set_stream(hj3d_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = ctx-owned stream */
+int hj3d_ctx_set_option(hj3d_ctx* ctx, int option, int64_t value);
+int hj3d_ctx_sync(hj3d_ctx* ctx);
+int hj3d_ctx_timings(hj3d_ctx* ctx, hj3d_timings* out);
+
+/* ---- build side ----------------------------------------------------------------------------
+ * hj3d_table_create  <- HtChaining1 / HtNested1 constructors via AlgHashJoinBuild(aHashDirSize, ..)
+ *                       / AlgNestJoinBuild(aHashDirSize, .., ..)   (algebra.hh:566-569, 372-380;
+ *                       ht_chaining.hh:106-107, ht_nested.hh:255-259).  The reservoir chunk-size
+ *                       arguments have no device equivalent (node storage is prefix-sum allocated).
+ * hj3d_table_build   <- the build strand: AlgScan::run -> Alg{Hash,Nest}JoinBuild::step -> insert
+ *                       for every tuple of the relation (algebra.hh:259-269,574-577,386-389;
+ *                       ht_chaining.hh:181-196; ht_nested.hh:287-311).  Bulk: the table must be empty.
+ * hj3d_table_clear   <- clear_ht() / HtX::clear() (algebra.hh:398,583; ht_chaining.hh:250-258;
+ *                       ht_nested.hh:438-447)
+ * hj3d_table_stats   <- makeStatistics() + getRsv*Size() + memoryConsupmtion*()
+ */
+int hj3d_table_create(hj3d_ctx* ctx, int kind, uint64_t num_buckets, hj3d_table** out);
+int hj3d_table_build(hj3d_ctx* ctx, hj3d_table* t, const void* d_tuples, uint64_t n, hj3d_keyspec ks);
+int hj3d_table_clear(hj3d_ctx* ctx, hj3d_table* t);
+int hj3d_table_destroy(hj3d_ctx* ctx, hj3d_table* t);
+int hj3d_table_stats(hj3d_ctx* ctx, hj3d_table* t, hj3d_stats* out);
+int hj3d_table_size(hj3d_table* t, uint64_t* num_entries, uint64_t* num_groups); /* size(); #MainNodes */
+
+/* ---- probe side ----------------------------------------------------------------------------
+ * hj3d_probe_chaining <- the probe strand AlgScan::run -> AlgHashJoinProbe<.., IsBuildKeyUnique>::step
+ *                        (algebra.hh:625-659) with HtChaining1::findDirEntryByOther (ht_chaining.hh:236-248).
+ *                        Result pair = (probe row id, build row id)  [concatfun_t::eval(l, r)].
+ * hj3d_probe_nested   <- AlgNestJoinProbe::step (algebra.hh:435-459) with
+ *                        HtNested1::findMainNodeByOther (ht_nested.hh:354-382).
+ *                        Result pair = (probe row id, group_ref); group_ref names the MainNode
+ *                        (one per distinct build key).  The checksum is taken over
+ *                        (probe row id, row id of the MainNode's own tuple) because group_ref
+ *                        values depend on the physical layout.
+ * hj3d_unnest         <- AlgUnnestHt::step (algebra.hh:510-541): (left, group_ref) ->
+ *                        (left, build row id) for the MainNode's tuple and every SubNode.
+ *                        `left` is an opaque uint32 carried through (deferred unnesting:
+ *                        main_experiment4.cc:846-867 chains two of these).
+ *
+ * d_gather (nullable): indirection for probe inputs that are intermediates: probe tuple i is
+ * d_probe[d_gather[i]] and the emitted left id is i (HashfunNestedRS reaches the key through
+ * _r, main_experiment4.cc:413-419).
+ * d_out_pairs (nullable = count only): uint32 pairs, order unspecified.
+ */
+int hj3d_probe_chaining(hj3d_ctx* ctx, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks,
+                        const uint32_t* d_gather, int build_key_unique, uint32_t flags,
+                        uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
+int hj3d_probe_nested(hj3d_ctx* ctx, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks,
+                      const uint32_t* d_gather, uint32_t flags,
+                      uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
+int hj3d_unnest(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_left, const uint32_t* d_group_ref, uint64_t n,
+                uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
+/* first build row id (the MainNode's own tuple) of each group_ref: d_out[i] = data(group d_group_ref[i]) */
+int hj3d_group_first_row(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_group_ref, uint64_t n, uint32_t* d_out);
+/* d_dst[i] = d_src[2*d_idx_pairs_col...]: small column helpers for composing deferred-unnest pipelines */
+int hj3d_gather_u32(hj3d_ctx* ctx, const uint32_t* d_src, const uint32_t* d_idx, uint64_t n, uint32_t* d_dst);
+int hj3d_split_pairs(hj3d_ctx* ctx, const uint32_t* d_pairs, uint64_t n, uint32_t* d_left, uint32_t* d_right);
+
+/* ---- whole join with HOST buffers (what a caller holding std::vector<tuple_t> relations does) --
+ * One call = build strand + probe strand (+ unnest) of one plan, host->device copies of both
+ * relations and the device->host copy of the result inside.  mode: 0 chaining, 1 chaining with
+ * IsBuildKeyUnique, 2 nested (no unnest), 3 nested + unnest  (plans Crs/CsrUU, Csr, NrsNU, Nrs/Nsr
+ * of main_experiment1.cc:624-1285).  h_out_pairs nullable.  stats nullable. */
+int hj3d_join_host(hj3d_ctx* ctx, int mode,
+                   const void* h_build, uint64_t n_build, hj3d_keyspec ks_build, uint64_t num_buckets,
+                   const void* h_probe, uint64_t n_probe, hj3d_keyspec ks_probe, uint32_t flags,
+                   uint32_t* h_out_pairs, uint64_t out_cap,
+                   hj3d_counters* probe_out, hj3d_counters* unnest_out, hj3d_stats* stats_out);
+
+/* ---- multi-GPU sharding (no reference equivalent) ---------------------------
+ * owner(tuple) = bucket(tuple) / ceil(num_buckets / n_owners): contiguous bucket ranges, so every
+ * bucket (chain, key group) lives on exactly one GPU.  Writes (key, global row id) pairs grouped by
+ * owner into d_out (key_bytes + 4 bytes each, 8 or 16 byte records) and the per-owner counts
+ * (host array of n_owners).  rowid_base is added to the local row position. */
+int hj3d_partition_by_owner(hj3d_ctx* ctx, const void* d_tuples, uint64_t n, hj3d_keyspec ks,
+                            uint64_t num_buckets, uint32_t n_owners, uint32_t rowid_base,
+                            void* d_out, uint64_t* h_counts);
+/* bucket range [lo, hi) owned by `owner` */
+int hj3d_owner_range(uint64_t num_buckets, uint32_t n_owners, uint32_t owner, uint64_t* lo, uint64_t* hi);
+/* a shard table holds only buckets [bucket_lo, bucket_hi) of a num_buckets wide directory */
+int hj3d_table_create_shard(hj3d_ctx* ctx, int kind, uint64_t num_buckets, uint64_t bucket_lo, uint64_t bucket_hi,
+                            hj3d_table** out);
+/* merge shard statistics exactly (Aggregate is mergeable: min,max,sum,sumsq,count) */
+int hj3d_stats_merge(const hj3d_stats* parts, uint32_t n, hj3d_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HJ3D_H */

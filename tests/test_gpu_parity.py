@@ -1,0 +1,305 @@
+"""GPU parity tests (the gate): the CUDA engine, called through the C ABI, against the CPU oracle on
+identical inputs -- bit-exact counters (count, numCmps), HtStatistics, and the result multiset."""
+import numpy as np
+import pytest
+
+import pyoracle as pyo
+from helpers import (assert_plan_equal, exp1_relations, exp4_relations, gpu_plan, load_golden, oracle_plan,
+                     sorted_pairs, sub, to_dev)
+from test_oracle import EXP1, LAYOUTS, exp1_plan_args, rand_case
+
+pytestmark = pytest.mark.gpu
+
+
+def KSg(pkg, tb, ko, kb=4, hid=0, ro=0xFFFFFFFF):
+    return pkg.KeySpec(tb, ko, kb, hid, ro)
+
+
+def both(pkg, ctx, oracle, mode, B, ks_b, D, P, ks_p, gather=None):
+    tb, ko, kb, hid = ks_b; tb2, ko2, kb2, hid2 = ks_p
+    o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(tb, ko, kb, hid), D, P, pyo.KeySpec(tb2, ko2, kb2, hid2), gather)
+    g = gpu_plan(pkg, ctx, mode, B, KSg(pkg, tb, ko, kb, hid), D, P, KSg(pkg, tb2, ko2, kb2, hid2), gather)
+    return g, o
+
+
+@pytest.mark.parametrize("name", EXP1)
+@pytest.mark.parametrize("plan", ["Csr", "CsrUU", "Crs", "Nsr", "Nrs", "NrsNU"])
+def test_exp1_plans_match_reference_goldens(pkg, ctx, oracle, name, plan):
+    """main_experiment1 plans on the reference's own generated relations; expected values are the
+    reference's (fixture) AND the oracle's."""
+    z, meta = load_golden(name)
+    R, S = exp1_relations(z)
+    mode, B, ksB, D, P, ksP = exp1_plan_args(R, S, meta, plan)
+    kb = (ksB.tuple_bytes, ksB.key_offset, 4, 0); kp = (ksP.tuple_bytes, ksP.key_offset, 4, 0)
+    g, o = both(pkg, ctx, oracle, mode, B, kb, D, P, kp)
+    assert_plan_equal(g, o, f"{name}/{plan}")
+    gold = meta["plans"][plan]
+    assert g["stats"] == gold["stats"]
+    assert g["probe"]["matches"] == gold["probe"]["matches"] and g["probe"]["num_cmps"] == gold["probe"]["num_cmps"]
+    if mode == 3:
+        assert sub(g["unnest"]) == sub(gold["unnest"])
+    else:
+        assert sub(g["probe"]) == sub(gold["probe"])
+    if mode <= 1:
+        assert sub(g["probe_count_only"]) == sub(g["probe"])   # count-only and materialising runs agree
+
+
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+@pytest.mark.parametrize("shape", [(0, 50, 10, 7), (300, 0, 10, 7), (1, 1, 1, 1), (500, 400, 50, 1), (2000, 3000, 300, 257),
+                                   (4000, 1000, 5000, 1024), (3000, 3000, 40, 4096), (50000, 70000, 20000, 33333),
+                                   (100000, 20000, 3, 5)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_random_relations_all_layouts(pkg, ctx, oracle, layout, shape, mode):
+    """empty / ragged / single-bucket / heavy-duplicate / non power-of-two directories, uint32, int32->murmur64
+    and uint64 keys; IsBuildKeyUnique on NON-unique keys follows the chain order of the reference."""
+    nB, nP, kmax, D = shape
+    tb, kb, hid, dt = LAYOUTS[layout]
+    if shape[0] >= 50000 and mode == 2:
+        pytest.skip("python-side group translation is slow; covered by mode 3")
+    rng = np.random.default_rng(hash((layout, shape)) % 2**32)
+    B, P = rand_case(rng, LAYOUTS[layout], nB, nP, kmax, D)
+    if hid == 2:
+        B -= kmax // 2; P -= kmax // 2
+    if hid == 1:
+        B = B * np.uint64(0x9E3779B97F4A7C15); P = P * np.uint64(0x9E3779B97F4A7C15)
+    g, o = both(pkg, ctx, oracle, mode, B, (tb, kb, kb, hid), D, P, (tb, 0, kb, hid))
+    assert_plan_equal(g, o, f"{layout}/{shape}/mode{mode}")
+
+
+def test_zipf_heavy_hitter(pkg, ctx, oracle):
+    """one key owning ~30% of the build side (atomic hot spot, one huge chain / key group)."""
+    rng = np.random.default_rng(11)
+    nB, nP = 200000, 5000
+    keys = rng.zipf(1.3, nB).astype(np.uint64) % 5000
+    B = np.zeros((nB, 3), np.uint32); B[:, 1] = keys.astype(np.uint32); B[:, 0] = np.arange(nB)
+    P = np.zeros((nP, 3), np.uint32); P[:, 0] = rng.permutation(nP)
+    D = len(np.unique(B[:, 1]))
+    for mode in (0, 3):
+        g, o = both(pkg, ctx, oracle, mode, B, (12, 4, 4, 0), D, P, (12, 0, 4, 0))
+        assert_plan_equal(g, o, f"zipf/mode{mode}")
+
+
+def test_gather_indirection(pkg, ctx, oracle):
+    rng = np.random.default_rng(5)
+    B = rng.integers(0, 200, (1000, 2)).astype(np.uint32)
+    P = rng.integers(0, 200, (300, 2)).astype(np.uint32)
+    gth = rng.integers(0, 300, 777).astype(np.uint32)
+    for mode in (0, 1, 2, 3):
+        g, o = both(pkg, ctx, oracle, mode, B, (8, 4, 4, 0), 97, P, (8, 0, 4, 0), gather=gth)
+        assert_plan_equal(g, o, f"gather/mode{mode}")
+
+
+def test_output_overflow_is_reported_and_counters_stay_exact(pkg, ctx, oracle):
+    import torch
+    rng = np.random.default_rng(3)
+    B = rng.integers(0, 50, (2000, 2)).astype(np.uint32)
+    P = rng.integers(0, 50, (500, 2)).astype(np.uint32)
+    o = oracle_plan(oracle, pyo, 0, B, pyo.KeySpec(8, 4), 31, P, pyo.KeySpec(8, 0))
+    t = ctx.table(pkg.CHAINING, 31).build(to_dev(B), len(B), KSg(pkg, 8, 4))
+    cap = o["probe"]["out_tuples"] // 3
+    out = torch.zeros((cap, 2), dtype=torch.int32, device="cuda")
+    rc, c = t.probe_chaining(to_dev(P), len(P), KSg(pkg, 8, 0), out=out, out_cap=cap)
+    assert rc == pkg.capi.OVERFLOW and c["overflow"] == 1 and c["out_written"] == cap
+    assert sub(c) == sub(o["probe"])
+    got = sorted_pairs(out.cpu().numpy().view(np.uint32))
+    assert np.all(np.isin(got, sorted_pairs(o["pairs"])))          # what was written is part of the result
+
+
+def test_clear_and_rebuild_like_repeat_mintime(pkg, ctx, oracle):
+    """clear_ht() between repetitions (main_experiment1.cc:675): same table object, same results."""
+    rng = np.random.default_rng(9)
+    B = rng.integers(0, 500, (3000, 3)).astype(np.uint32)
+    P = rng.integers(0, 500, (1000, 3)).astype(np.uint32)
+    o = oracle_plan(oracle, pyo, 0, B, pyo.KeySpec(12, 4), 211, P, pyo.KeySpec(12, 0))
+    t = ctx.table(pkg.CHAINING, 211)
+    dB, dP = to_dev(B), to_dev(P)
+    for _ in range(3):
+        t.build(dB, len(B), KSg(pkg, 12, 4))
+        with pytest.raises(pkg.Hj3dError):
+            t.build(dB, len(B), KSg(pkg, 12, 4))                   # bulk build into a non-empty table
+        rc, c = t.probe_chaining(dP, len(P), KSg(pkg, 12, 0))
+        assert sub(c) == sub(o["probe"]) and t.stats() == o["stats"]
+        t.clear()
+    s = t.stats()
+    assert s["num_empty"] == 211 and s["num_entries"] == 0
+
+
+def test_error_behaviour(pkg, ctx):
+    with pytest.raises(pkg.Hj3dError):
+        ctx.table(pkg.CHAINING, 0)                                  # h % 0
+    t = ctx.table(pkg.NESTED, 8)
+    B = np.zeros((4, 2), np.uint32)
+    with pytest.raises(pkg.Hj3dError):
+        t.probe_nested(to_dev(B), 4, KSg(pkg, 8, 0))                # not built
+    t.build(to_dev(B), 4, KSg(pkg, 8, 0))
+    with pytest.raises(pkg.Hj3dError):
+        t.probe_chaining(to_dev(B), 4, KSg(pkg, 8, 0))              # wrong table kind
+    with pytest.raises(pkg.Hj3dError):
+        t.probe_nested(to_dev(B), 4, KSg(pkg, 8, 0, 4, 2))          # different hash function than the build side
+    with pytest.raises(pkg.Hj3dError):
+        t.build(to_dev(B), 4, KSg(pkg, 8, 6))                       # key outside / misaligned
+
+
+def gpu_exp4(pkg, ctx, R, S, T, D):
+    """Ndu and Chj (main_experiment4.cc:831-1043) composed from the C-ABI operators on the device."""
+    import torch
+    ksR, ksF = KSg(pkg, 8, 0), KSg(pkg, 8, 4)
+    dR, dS, dT = to_dev(R), to_dev(S), to_dev(T)
+    i32 = dict(dtype=torch.int32, device="cuda")
+    res = {}
+    tS = ctx.table(pkg.NESTED, D).build(dS, len(S), ksF)
+    tT = ctx.table(pkg.NESTED, D).build(dT, len(T), ksF)
+    n1 = torch.zeros((len(R), 2), **i32)
+    _, c1 = tS.probe_nested(dR, len(R), ksR, out=n1, out_cap=len(R))
+    m1 = c1["out_written"]
+    r1, sg1 = n1[:m1, 0].contiguous(), n1[:m1, 1].contiguous()
+    n2 = torch.zeros((max(m1, 1), 2), **i32)
+    _, c2 = tT.probe_nested(dR, m1, ksR, gather=r1, out=n2, out_cap=m1)      # key reached through r (HashfunNestedRS)
+    m2 = c2["out_written"]
+    i2, tg2 = n2[:m2, 0].contiguous(), n2[:m2, 1].contiguous()
+    _, u1 = tT.unnest(i2, tg2, m2, flags=0)
+    f1 = torch.zeros((max(u1["out_tuples"], 1), 2), **i32)
+    _, u1 = tT.unnest(i2, tg2, m2, out=f1, out_cap=u1["out_tuples"])          # (idx into n1, t)
+    k1 = u1["out_written"]
+    idx1, trow = f1[:k1, 0].contiguous(), f1[:k1, 1].contiguous()
+    sg = torch.zeros(max(k1, 1), **i32)
+    ctx.gather_u32(sg1, idx1, k1, sg)
+    seq = torch.arange(k1, **i32)
+    _, u2 = tS.unnest(seq, sg, k1, flags=0)
+    f2 = torch.zeros((max(u2["out_tuples"], 1), 2), **i32)
+    _, u2 = tS.unnest(seq, sg, k1, out=f2, out_cap=u2["out_tuples"])          # (idx into f1, s)
+    ctx.sync()
+    f2n = f2[:u2["out_written"]].cpu().numpy().view(np.uint32)
+    f1n = f1[:k1].cpu().numpy().view(np.uint32); n1n = n1[:m1].cpu().numpy().view(np.uint32)
+    r = n1n[f1n[f2n[:, 0], 0], 0]; t = f1n[f2n[:, 0], 1]; s = f2n[:, 1]
+    res["Ndu"] = dict(c_probe_RS=c1["matches"], c_probe_RS_cmp=c1["num_cmps"], c_probe_RT=c2["matches"],
+                      c_probe_RT_cmp=c2["num_cmps"], c_unnest1=u1["out_tuples"], c_unnest2=u2["out_tuples"],
+                      c_top=len(f2n)), (r, s, t)
+    cS = ctx.table(pkg.CHAINING, D).build(dS, len(S), ksF)
+    cT = ctx.table(pkg.CHAINING, D).build(dT, len(T), ksF)
+    _, c1 = cS.probe_chaining(dR, len(R), ksR, flags=0)
+    p1 = torch.zeros((max(c1["out_tuples"], 1), 2), **i32)
+    _, c1 = cS.probe_chaining(dR, len(R), ksR, out=p1, out_cap=c1["out_tuples"])
+    m1 = c1["out_written"]
+    r1 = p1[:m1, 0].contiguous()
+    _, c2 = cT.probe_chaining(dR, m1, ksR, gather=r1, flags=0)
+    p2 = torch.zeros((max(c2["out_tuples"], 1), 2), **i32)
+    _, c2 = cT.probe_chaining(dR, m1, ksR, gather=r1, out=p2, out_cap=c2["out_tuples"])
+    ctx.sync()
+    p1n = p1[:m1].cpu().numpy().view(np.uint32); p2n = p2[:c2["out_written"]].cpu().numpy().view(np.uint32)
+    r = p1n[p2n[:, 0], 0]; s = p1n[p2n[:, 0], 1]; t = p2n[:, 1]
+    res["Chj"] = dict(c_probe_RS=c1["matches"], c_probe_RS_cmp=c1["num_cmps"], c_probe_RT=c2["matches"],
+                      c_probe_RT_cmp=c2["num_cmps"], c_unnest1=0, c_unnest2=0, c_top=len(p2n)), (r, s, t)
+    return res
+
+
+@pytest.mark.parametrize("name", ["exp4_R12_a4_b3_A5_B7", "exp4_R10_a2_b2_A10_B1"])
+def test_exp4_deferred_unnesting_matches_reference(pkg, ctx, oracle, name):
+    z, meta = load_golden(name)
+    R, S, T = exp4_relations(z, meta)
+    got = gpu_exp4(pkg, ctx, R, S, T, meta["D"])
+    mix = np.vectorize(lambda a, b: oracle.pair_mix(int(a), int(b)), otypes=[np.uint64])
+    for plan in ("Ndu", "Chj"):
+        counts, (r, s, t) = got[plan]
+        ms = mix(mix(r, s) & np.uint64(0xFFFFFFFF), t)
+        counts["checksum_sum"] = int(ms.sum(dtype=np.uint64)); counts["checksum_xor"] = int(np.bitwise_xor.reduce(ms))
+        assert counts == meta[plan], plan
+    assert np.array_equal(np.sort(got["Ndu"][1][0]), np.sort(got["Chj"][1][0]))
+
+
+def test_algebra_example(pkg, ctx):
+    """main_algebra_example.cc algebra_test1..3 (int attributes hashed with murmur64, 5 buckets)."""
+    z, meta = load_golden("algebra_example")
+    L, Rr = z["L"], z["R"]
+    Lsel = np.ascontiguousarray(L[L[:, 1] < 40])                   # AlgSelection<SelectionL> on the host side
+    ks = (8, 0, 4, 2)
+    g2 = gpu_plan(pkg, ctx, 3, Rr, KSg(pkg, *ks), 5, Lsel, KSg(pkg, *ks))
+    assert np.array_equal(sorted_pairs(g2["pairs"]), sorted_pairs(meta["test2_nested_unnest"]["pairs"]))
+    assert g2["probe"]["matches"] == 3 and g2["unnest"]["out_tuples"] == 6
+    assert g2["stats"] == meta["test1_nested_nu"]["stats"]
+    g3 = gpu_plan(pkg, ctx, 0, Rr, KSg(pkg, *ks), 5, Lsel, KSg(pkg, *ks))
+    assert np.array_equal(sorted_pairs(g3["pairs"]), sorted_pairs(meta["test3_chaining"]["pairs"]))
+    assert sub(g3["probe"]) == sub(meta["test3_chaining"]["probe"]) and g3["stats"] == meta["test3_chaining"]["stats"]
+
+
+def test_join_host_entry_point(pkg, ctx, oracle):
+    """hj3d_join_host: host buffers in, host result out (the e2e call of bench.py)."""
+    rng = np.random.default_rng(21)
+    nR, nS = 5000, 40000
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR, nS)
+    for mode, (B, kb, P, kp, D) in {1: (R, 0, S, 4, nR), 0: (S, 4, R, 0, 3000), 3: (S, 4, R, 0, 3000), 2: (S, 4, R, 0, 3000)}.items():
+        o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(12, kb), D, P, pyo.KeySpec(12, kp))
+        cap = nS
+        out = np.zeros((cap, 2), np.uint32)
+        rc, pc, uc, st = ctx.join_host(mode, B, len(B), KSg(pkg, 12, kb), D, P, len(P), KSg(pkg, 12, kp),
+                                       flags=pkg.F_CHECKSUM, h_out=out, out_cap=cap, want_stats=True)
+        assert rc == 0 and st == o["stats"]
+        assert pc["matches"] == o["probe"]["matches"] and pc["num_cmps"] == o["probe"]["num_cmps"]
+        if mode == 3:
+            assert sub(uc) == sub(o["unnest"])
+            assert np.array_equal(sorted_pairs(out[:uc["out_written"]]), sorted_pairs(o["pairs"]))
+        elif mode <= 1:
+            assert sub(pc) == sub(o["probe"])
+            assert np.array_equal(sorted_pairs(out[:pc["out_written"]]), sorted_pairs(o["pairs"]))
+
+
+def test_partition_by_owner_and_sharded_join(pkg, ctx, oracle):
+    """Multi-GPU sharding emulated on one device: partition both relations by bucket-range owner, build one
+    shard table per owner from (key, global row id) records, probe each shard with its own partition,
+    merge -- must equal the unsharded reference result bit-exactly."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(33)
+    nR, nS, G, D = 20000, 90000, 4, 7001
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR, nS)
+    lib = pkg.capi.load()
+    for mode in (1, 3):
+        B, kb, P, kp = (R, 0, S, 4) if mode == 1 else (S, 4, R, 0)
+        o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(12, kb), D, P, pyo.KeySpec(12, kp))
+        dB, dP = to_dev(B), to_dev(P)
+        pb = torch.zeros((len(B), 2), dtype=torch.int32, device="cuda")
+        pp = torch.zeros((len(P), 2), dtype=torch.int32, device="cuda")
+        cb = ctx.partition_by_owner(dB, len(B), KSg(pkg, 12, kb), D, G, 0, pb)
+        cp = ctx.partition_by_owner(dP, len(P), KSg(pkg, 12, kp), D, G, 0, pp)
+        assert sum(cb) == len(B) and sum(cp) == len(P)
+        ks_rec = KSg(pkg, 8, 0, 4, 0, 4)                              # (key, global row id) records
+        tot = {k: 0 for k in ("matches", "num_cmps", "checksum_sum", "checksum_xor", "out_tuples")}
+        parts = (pkg.Stats * G)()
+        pairs, ob, op = [], 0, 0
+        for g in range(G):
+            lo, hi = C.c_uint64(), C.c_uint64()
+            lib.hj3d_owner_range(D, G, g, C.byref(lo), C.byref(hi))
+            t = ctx.table(pkg.CHAINING if mode == 1 else pkg.NESTED, D, shard=(lo.value, hi.value))
+            t.build(pb[ob:ob + cb[g]].contiguous(), cb[g], ks_rec)
+            probe_part = pp[op:op + cp[g]].contiguous()
+            if mode == 1:
+                out = torch.zeros((max(cp[g], 1), 2), dtype=torch.int32, device="cuda")
+                _, c = t.probe_chaining(probe_part, cp[g], ks_rec, unique=True, out=out, out_cap=cp[g])
+                res = out[:c["out_written"]].cpu().numpy().view(np.uint32)
+                # left ids are positions inside the partition: translate to global row ids
+                glob = probe_part.cpu().numpy().view(np.uint32)[:, 1]
+                pairs.append(np.stack([glob[res[:, 0]], res[:, 1]], axis=1))
+                cc = c
+            else:
+                nest = torch.zeros((max(cp[g], 1), 2), dtype=torch.int32, device="cuda")
+                _, c = t.probe_nested(probe_part, cp[g], ks_rec, out=nest, out_cap=cp[g])
+                m = c["out_written"]
+                # carry the GLOBAL probe row id through the unnest as `left`
+                left = torch.zeros(max(m, 1), dtype=torch.int32, device="cuda")
+                ctx.gather_u32(probe_part[:, 1].contiguous(), nest[:m, 0].contiguous(), m, left)
+                _, u = t.unnest(left, nest[:m, 1].contiguous(), m, flags=0)
+                out = torch.zeros((max(u["out_tuples"], 1), 2), dtype=torch.int32, device="cuda")
+                _, u = t.unnest(left, nest[:m, 1].contiguous(), m, out=out, out_cap=u["out_tuples"])
+                pairs.append(out[:u["out_written"]].cpu().numpy().view(np.uint32))
+                cc = c
+            for k in ("matches", "num_cmps"):
+                tot[k] += cc[k]
+            parts[g] = pkg.Stats(**t.stats())
+            ob += cb[g]; op += cp[g]
+        merged = pkg.Stats()
+        lib.hj3d_stats_merge(parts, G, C.byref(merged))
+        assert merged.as_dict() == o["stats"]
+        assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"]
+        assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"]))
