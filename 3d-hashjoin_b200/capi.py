@@ -16,7 +16,7 @@ HASH_MURMUR32, HASH_MURMUR64, HASH_MURMUR64_SEXT32 = 0, 1, 2
 NO_ROWID = 0xFFFFFFFF
 F_CHECKSUM = 1
 F_DEVICE_RESULT = 2
-OPT_WARP_AGGREGATE, OPT_PARTITION_BYTES, OPT_PARTITION_WINDOW = 1, 2, 3
+OPT_WARP_AGGREGATE, OPT_PARTITION_BYTES, OPT_PARTITION_WINDOW, OPT_PARTITION_MIN_PROBE = 1, 2, 3, 4
 
 # every symbol include/hj3d.h declares (tests check that the library exports all of them)
 SYMBOLS = [

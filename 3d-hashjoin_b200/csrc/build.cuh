@@ -28,15 +28,18 @@ constexpr int kBuildTile    = kBuildThreads * kBuildItems;
 
 // ---- 1. histogram: off[b] += 1 for every build tuple -------------------------------------------
 template <int HASH, bool AGG>
-__global__ void __launch_bounds__(kBuildThreads) k_histogram(Src s, Dir d, uint32_t* __restrict__ off) {
+__global__ void __launch_bounds__(kBuildThreads) k_histogram(Src s, Dir d, const uint2* __restrict__ tilemap, uint32_t* __restrict__ off) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint64_t base = (uint64_t)blockIdx.x * kBuildTile + threadIdx.x;
+  uint64_t t0; uint32_t tn;
+  block_tile<kBuildTile>(tilemap, s.n, t0, tn);
 #pragma unroll
   for (int j = 0; j < kBuildItems; ++j) {
-    const uint64_t i = base + (uint64_t)j * kBuildThreads;
-    const bool ok = i < s.n;
+    const uint32_t li = j * kBuildThreads + threadIdx.x;
+    const uint64_t i = t0 + li;
+    const bool in = li < tn;
     uint32_t b = 0;
-    if (ok) b = HashT<HASH>::bucket(src_key<KeyT>(s, i), d) - d.lo;
+    bool ok = in;
+    if (in) { b = HashT<HASH>::bucket(src_key<KeyT>(s, i), d) - d.lo; ok = b < d.n_local; }   // shard tables skip foreign buckets
     if (AGG) {
       // warp-aggregated: one atomic per distinct bucket in the warp (hot keys of skewed inputs)
       const uint32_t act = __ballot_sync(0xffffffffu, ok);
@@ -56,15 +59,18 @@ __global__ void __launch_bounds__(kBuildThreads) k_histogram(Src s, Dir d, uint3
 // After the pass off[b] has been decremented chain-length times, i.e. holds the START of the run.
 template <int HASH, bool AGG>
 __global__ void __launch_bounds__(kBuildThreads)
-k_scatter(Src s, Dir d, uint32_t* __restrict__ off, Slot<typename HashT<HASH>::key_t>* __restrict__ slots) {
+k_scatter(Src s, Dir d, const uint2* __restrict__ tilemap, uint32_t* __restrict__ off,
+          Slot<typename HashT<HASH>::key_t>* __restrict__ slots) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint64_t base = (uint64_t)blockIdx.x * kBuildTile + threadIdx.x;
+  uint64_t t0; uint32_t tn;
+  block_tile<kBuildTile>(tilemap, s.n, t0, tn);
 #pragma unroll
   for (int j = 0; j < kBuildItems; ++j) {
-    const uint64_t i = base + (uint64_t)j * kBuildThreads;
-    const bool ok = i < s.n;
+    const uint32_t li = j * kBuildThreads + threadIdx.x;
+    const uint64_t i = t0 + li;
+    bool ok = li < tn;
     KeyT key = 0; uint32_t b = 0;
-    if (ok) { key = src_key<KeyT>(s, i); b = HashT<HASH>::bucket(key, d) - d.lo; }
+    if (ok) { key = src_key<KeyT>(s, i); b = HashT<HASH>::bucket(key, d) - d.lo; ok = b < d.n_local; }
     uint32_t pos = 0;
     if (AGG) {
       const uint32_t act = __ballot_sync(0xffffffffu, ok);

@@ -94,6 +94,18 @@ struct Src {
   uint32_t        rowid_off;  // HJ3D_NO_ROWID: row id = position
 };
 
+// A block's work: records [t0, t0 + tn).  tilemap == nullptr: block b owns tile b of the whole input;
+// otherwise the input is bucket-range partitioned with gaps and tilemap[b] = (first record, count).
+template <int TILE>
+__device__ __forceinline__ void block_tile(const uint2* __restrict__ tilemap, uint64_t n, uint64_t& t0, uint32_t& tn) {
+  if (tilemap) { const uint2 e = tilemap[blockIdx.x]; t0 = e.x; tn = e.y; }
+  else { t0 = (uint64_t)blockIdx.x * TILE; tn = (n - t0) < (uint64_t)TILE ? (uint32_t)(n - t0) : (uint32_t)TILE; }
+}
+
+// id reported as the `left` of a result pair: the tuple's own row id when it carries one (partitioned /
+// exchanged (key,row id) records), else its position in the probe sequence.
+__device__ __forceinline__ uint32_t src_leftid(const struct Src& s, uint64_t i);
+
 template <class KeyT>
 __device__ __forceinline__ KeyT src_key(const Src& s, uint64_t i) {
   uint64_t idx = s.gather ? (uint64_t)__ldg(s.gather + i) : i;
@@ -103,6 +115,11 @@ __device__ __forceinline__ uint32_t src_rowid(const Src& s, uint64_t i) {
   if (s.rowid_off == HJ3D_NO_ROWID) return (uint32_t)i;
   uint64_t idx = s.gather ? (uint64_t)__ldg(s.gather + i) : i;
   return __ldg(reinterpret_cast<const uint32_t*>(s.base + idx * s.stride + s.rowid_off));
+}
+
+__device__ __forceinline__ uint32_t src_leftid(const Src& s, uint64_t i) {
+  if (s.rowid_off == HJ3D_NO_ROWID || s.gather) return (uint32_t)i;
+  return __ldg(reinterpret_cast<const uint32_t*>(s.base + i * s.stride + s.rowid_off));
 }
 
 // (key, row id) slot of the bucket-ordered build side

@@ -41,7 +41,8 @@ struct hj3d_ctx {
   // options
   int64_t warp_aggregate = 1;
   int64_t partition_bytes = 48ll << 20;
-  int64_t partition_window = 16ll << 20;
+  int64_t partition_window = 8ll << 20;
+  int64_t partition_min_probe = 1ll << 20;
   // per-phase events of the last call
   cudaEvent_t ev[PH_COUNT][2];
   bool        ev_used[PH_COUNT];
@@ -53,6 +54,16 @@ struct hj3d_ctx {
   unsigned long long* d_scalar = nullptr;   // 4 scalars
   void*        h_pinned = nullptr;          // >= 256 B
   int          sm_count = 148;
+  // grow-only workspace for per-call temporaries: bump allocated, reset at the start of every call, so
+  // steady-state calls (the repeat loop of the drivers) never touch the device allocator
+  struct Chunk { uint8_t* base; size_t cap, used; };
+  std::vector<Chunk> arena;
+  struct HostJoinBufs { void *b = nullptr, *p = nullptr, *out = nullptr, *nest = nullptr, *l = nullptr, *g = nullptr;
+                        size_t cb = 0, cp = 0, cout = 0, cnest = 0, cl = 0, cg = 0; } hj;
+};
+
+struct Buf {  // persistent, grow-only device buffer owned by a table
+  void* p = nullptr; size_t cap = 0;
 };
 
 struct hj3d_table {
@@ -68,6 +79,8 @@ struct hj3d_table {
   uint32_t* goff = nullptr;                // [n_local + 1]     (nested)
   void*     groups = nullptr;              // Group<KeyT>[G]    (nested)
   uint32_t* rows = nullptr;                // [n]               (nested)
+  Buf       b_off, b_slots, b_goff, b_groups, b_rows;   // storage behind the pointers above (kept across clear())
+  uint32_t  parts = 1, part_width = 0;     // bucket-range partitioning used by the build (1 = none)
   DevStats  hstats{};                      // bucket statistics captured during the build
   bool      have_stats = false;
 };
@@ -88,15 +101,61 @@ inline void begin_call(hj3d_ctx* c) {
 }
 inline void end_call(hj3d_ctx* c) { cudaEventRecord(c->ev_total[1], c->stream); }
 
+int raw_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(HJ3D_ERR_NOMEM, "device out of memory"); }
+  if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  return HJ3D_OK;
+}
+
+// start of a call: all temporaries of the previous call are dead (every call ends with a stream sync or
+// only enqueues work that is ordered before the next call's work on the same stream).  If the previous
+// call had to add chunks, merge them into one so the next call of the same shape bump-allocates only.
+int arena_reset(hj3d_ctx* c) {
+  if (c->arena.size() > 1) {
+    size_t total = 0;
+    for (auto& k : c->arena) total += k.cap;
+    cudaStreamSynchronize(c->stream);
+    for (auto& k : c->arena) cudaFree(k.base);
+    c->arena.clear();
+    void* p = nullptr;
+    HJ_TRY(raw_alloc(&p, total));
+    c->arena.push_back({(uint8_t*)p, total, 0});
+  }
+  for (auto& k : c->arena) k.used = 0;
+  return HJ3D_OK;
+}
+
 template <class T> int dev_alloc(hj3d_ctx* c, T** p, uint64_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), c->stream);
-  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(HJ3D_ERR_NOMEM, "device out of memory"); }
-  if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+  const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+  for (auto& k : c->arena)
+    if (k.cap - k.used >= bytes) { *p = (T*)(k.base + k.used); k.used += bytes; return HJ3D_OK; }
+  const size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+  void* q = nullptr;
+  HJ_TRY(raw_alloc(&q, cap));
+  c->arena.push_back({(uint8_t*)q, cap, bytes});
+  *p = (T*)q;
   return HJ3D_OK;
 }
-inline void dev_free(hj3d_ctx* c, void* p) { if (p) cudaFreeAsync(p, c->stream); }
+inline void dev_free(hj3d_ctx*, void*) {}   // arena memory is reclaimed wholesale by arena_reset
+
+template <class T> int buf_ensure(hj3d_ctx* c, Buf& b, T** p, uint64_t count) {
+  if (count == 0) count = 1;
+  const size_t bytes = count * sizeof(T);
+  if (b.cap < bytes) {
+    if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    HJ_TRY(raw_alloc(&b.p, bytes));
+    b.cap = bytes;
+  }
+  *p = (T*)b.p;
+  return HJ3D_OK;
+}
+inline void buf_release(hj3d_ctx* c, Buf& b) {
+  if (b.p) { if (c) cudaStreamSynchronize(c->stream); cudaFree(b.p); }
+  b.p = nullptr; b.cap = 0;
+}
 
 inline uint32_t blocks_for(uint64_t n, uint32_t per_block) { return (uint32_t)((n + per_block - 1) / per_block); }
 
@@ -162,10 +221,95 @@ void init_dev_stats_host(DevStats& s) {
   s.all = DevAgg{~0ull, 0, 0, 0, 0}; s.nonempty = DevAgg{~0ull, 0, 0, 0, 0}; s.empty = 0;
 }
 
-void free_table_arrays(hj3d_ctx* c, hj3d_table* t) {
-  dev_free(c, t->off); dev_free(c, t->slots); dev_free(c, t->goff); dev_free(c, t->groups); dev_free(c, t->rows);
+// clear(): the table becomes empty but keeps its device buffers for the next build of the repeat loop
+void clear_table(hj3d_table* t) {
   t->off = nullptr; t->slots = nullptr; t->goff = nullptr; t->groups = nullptr; t->rows = nullptr;
-  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false;
+  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false; t->parts = 1; t->part_width = 0;
+}
+void free_table_arrays(hj3d_ctx* c, hj3d_table* t) {
+  clear_table(t);
+  buf_release(c, t->b_off); buf_release(c, t->b_slots); buf_release(c, t->b_goff); buf_release(c, t->b_groups);
+  buf_release(c, t->b_rows);
+}
+
+// ---- bucket-range partitioning inside one GPU ---------------------------------------------------------
+// The records of partition p live in recs[part_start[p] .. part_start[p] + counts[p]) (regions may have
+// gaps); tile maps translate block ids of the build / probe kernels to record ranges.
+template <class KeyT> struct Partitioned {
+  Slot<KeyT>* recs = nullptr;
+  unsigned long long* part_start = nullptr;   // device [P]
+  unsigned long long* counts = nullptr;       // device [P]
+  uint32_t P = 0;
+  uint64_t n_kept = 0;                        // records inside the (shard) directory
+  bool     fallback = false;
+};
+
+inline uint32_t choose_parts(hj3d_ctx* c, uint64_t table_bytes, uint64_t n_local) {
+  if (c->partition_bytes <= 0 || (int64_t)table_bytes <= c->partition_bytes) return 1;
+  uint64_t want = (table_bytes + c->partition_window - 1) / c->partition_window;
+  uint32_t P = 1;
+  while (P < want && P < (uint32_t)kMaxParts) P <<= 1;
+  while (P > 1 && (uint64_t)P > n_local) P >>= 1;
+  return P;
+}
+
+template <int HASH, bool LEFTID>
+int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uint32_t rowid_base,
+                    Partitioned<typename HashT<HASH>::key_t>* out) {
+  using KeyT = typename HashT<HASH>::key_t;
+  PhaseTimer pt(c, PH_PARTITION);
+  const uint64_t n = src.n;
+  const PartFn pf = make_partfn(width, d.lo);
+  const unsigned long long cap = n / P + n / (32ull * P) + 8192;          // expected size + ~3% + constant slack
+  out->P = P;
+  HJ_TRY(dev_alloc(c, &out->recs, (uint64_t)P * cap));
+  HJ_TRY(dev_alloc(c, &out->part_start, P));
+  HJ_TRY(dev_alloc(c, &out->counts, P));
+  CUDA_TRY(cudaMemsetAsync(out->counts, 0, (size_t)P * 8, c->stream));
+  k_part_fixed_starts<<<blocks_for(P, 256), 256, 0, c->stream>>>(P, cap, out->part_start);
+  const uint32_t nb = blocks_for(n, kPartTile);
+  if (nb) k_part_scatter<HASH, LEFTID><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, P, rowid_base, cap, out->part_start, out->counts, out->recs);
+  c->launches += nb ? 2 : 1;
+  unsigned long long* h = (unsigned long long*)c->h_pinned;               // P <= 1024 -> 8 KB
+  CUDA_TRY(cudaMemcpyAsync(h, out->counts, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  bool overflow = false; uint64_t kept = 0;
+  for (uint32_t p = 0; p < P; ++p) { kept += h[p]; overflow |= h[p] > cap; }
+  out->n_kept = kept;
+  if (overflow) {
+    // skewed partition sizes: the cursors hold the exact histogram, redo the scatter into exact regions
+    out->fallback = true;
+    unsigned long long* counts2 = nullptr;
+    HJ_TRY(dev_alloc(c, &counts2, P));
+    k_part_prefix<<<1, 32, 0, c->stream>>>(out->counts, P, out->part_start);
+    CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)P * 8, c->stream));
+    k_part_scatter<HASH, LEFTID><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, P, rowid_base, ~0ull, out->part_start, counts2, out->recs);
+    c->launches += 2;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+template <class KeyT>
+int make_tilemap(hj3d_ctx* c, const Partitioned<KeyT>& pr, uint32_t tile, uint2** tilemap, uint32_t* n_tiles) {
+  uint32_t* tile_prefix = nullptr;
+  HJ_TRY(dev_alloc(c, &tile_prefix, (uint64_t)pr.P + 1));
+  k_tile_prefix<<<1, 1024, 0, c->stream>>>(pr.counts, pr.P, tile, tile_prefix);
+  uint32_t* h = (uint32_t*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, tile_prefix + pr.P, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *n_tiles = *h;
+  HJ_TRY(dev_alloc(c, tilemap, (uint64_t)*n_tiles));
+  k_make_tilemap<<<pr.P, 256, 0, c->stream>>>(pr.part_start, pr.counts, tile_prefix, tile, *tilemap);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+template <class KeyT> Src records_src(const Partitioned<KeyT>& pr) {
+  Src s; s.base = (const uint8_t*)pr.recs; s.gather = nullptr; s.n = 0; s.stride = sizeof(Slot<KeyT>);
+  s.key_off = 0; s.rowid_off = sizeof(KeyT);
+  return s;
 }
 
 // ---- build ----------------------------------------------------------------------------------------
@@ -176,18 +320,43 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   const uint32_t nl = t->dir.n_local;
   const Dir d = t->dir;
   const bool agg = c->warp_aggregate != 0;
-  HJ_TRY(dev_alloc(c, &t->off, (uint64_t)nl + 1));
+  HJ_TRY(buf_ensure(c, t->b_off, &t->off, (uint64_t)nl + 1));
   Slot<KeyT>* slots = nullptr;
-  HJ_TRY(dev_alloc(c, &slots, n));
+  if (t->kind == HJ3D_CHAINING) HJ_TRY(buf_ensure(c, t->b_slots, &slots, n));
+  else                          HJ_TRY(dev_alloc(c, &slots, n));          // nested: only needed during the build
   t->slots = slots;
+
+  // bucket-order the input first when the directory + slots do not fit the L2 window budget
+  const uint64_t table_bytes = (uint64_t)nl * 4 + n * sizeof(Slot<KeyT>);
+  uint32_t P = choose_parts(c, table_bytes, nl);
+  uint32_t width = (uint32_t)(((uint64_t)nl + P - 1) / P);
+  if ((double)n * 1.04 + 8192.0 * P >= 4.0e9) P = 1;                      // tile maps address records with 32 bits
+  Partitioned<KeyT> pr;
+  const uint2* tilemap = nullptr;
+  uint32_t n_tiles = blocks_for(n, kBuildTile);
+  Src bsrc = src;
+  uint64_t n_in = n;
+  if (P > 1 && n) {
+    HJ_TRY((partition_local<HASH, false>(c, src, d, P, width, 0, &pr)));
+    uint2* tm = nullptr;
+    HJ_TRY(make_tilemap(c, pr, kBuildTile, &tm, &n_tiles));
+    tilemap = tm;
+    bsrc = records_src(pr);
+    n_in = pr.n_kept;
+    t->parts = P; t->part_width = width;
+  } else {
+    P = 1;
+    t->parts = 1; t->part_width = nl ? nl : 1;
+  }
+  (void)n_in;
   DevStats hs; init_dev_stats_host(hs);
-  CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));  // hs copied synchronously into the driver's staging
+  CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
   {
     PhaseTimer pt(c, PH_HIST);
     CUDA_TRY(cudaMemsetAsync(t->off, 0, ((uint64_t)nl + 1) * 4, c->stream));
-    if (n) {
-      if (agg) k_histogram<HASH, true><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off);
-      else     k_histogram<HASH, false><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off);
+    if (n_tiles) {
+      if (agg) k_histogram<HASH, true><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off);
+      else     k_histogram<HASH, false><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off);
       ++c->launches;
     }
   }
@@ -202,9 +371,9 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   }
   {
     PhaseTimer pt(c, PH_SCATTER);
-    if (n) {
-      if (agg) k_scatter<HASH, true><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off, slots);
-      else     k_scatter<HASH, false><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(src, d, t->off, slots);
+    if (n_tiles) {
+      if (agg) k_scatter<HASH, true><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off, slots);
+      else     k_scatter<HASH, false><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off, slots);
       ++c->launches;
     }
   }
@@ -224,16 +393,16 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     unsigned long long* d_tot = c->d_scalar;
     HJ_TRY((run_scan<unsigned long long, false>(c, LoadCells{cell, gcnt, n}, StoreCells{gidx, gstart}, n + 1,
                                                   (DevStats*)nullptr, d_tot)));
-    unsigned long long tot = 0;
-    CUDA_TRY(cudaMemcpyAsync(&tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long* h_tot = (unsigned long long*)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const uint64_t G = tot >> 32;
+    const uint64_t G = *h_tot >> 32;
     t->n_groups = G;
     Group<KeyT>* groups = nullptr;
-    HJ_TRY(dev_alloc(c, &groups, G));
+    HJ_TRY(buf_ensure(c, t->b_groups, &groups, G));
     t->groups = groups;
-    HJ_TRY(dev_alloc(c, &t->goff, (uint64_t)nl + 1));
-    HJ_TRY(dev_alloc(c, &t->rows, n));
+    HJ_TRY(buf_ensure(c, t->b_goff, &t->goff, (uint64_t)nl + 1));
+    HJ_TRY(buf_ensure(c, t->b_rows, &t->rows, n));
     if (n) {
       k_group_emit<HASH><<<blocks_for(n, 256), 256, 0, c->stream>>>(slots, n, cell, gcnt, gmin, gidx, gstart, groups);
       ++c->launches;
@@ -250,10 +419,7 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     HJ_TRY(dev_alloc(c, &dummy, nb));
     k_scan_reduce<uint32_t, LoadDiff, true><<<nb, kScanThreads, 0, c->stream>>>(LoadDiff{t->goff}, nl, dummy, c->d_stats);
     ++c->launches;
-    dev_free(c, dummy);
-    dev_free(c, cell); dev_free(c, rep); dev_free(c, gcnt); dev_free(c, gmin); dev_free(c, gidx); dev_free(c, gstart);
-    // the (key,row) slots are only needed for the chaining probe
-    dev_free(c, t->slots); t->slots = nullptr;
+    t->slots = nullptr;                                                   // arena memory, dead after this call
   }
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaGetLastError());
@@ -275,14 +441,35 @@ int fetch_counters(hj3d_ctx* c, hj3d_counters* out, uint64_t out_cap, bool wrote
   return HJ3D_OK;
 }
 
+// Probe inputs are bucket-ordered with the table's own partition function when the table was built
+// partitioned (its directory does not fit the L2 budget) and the probe side is large enough to pay
+// for the extra pass; inputs read through a gather index are probed in place.
+template <int HASH>
+int probe_source(hj3d_ctx* c, hj3d_table* t, Src& src, const uint2** tilemap, uint32_t* n_tiles) {
+  using KeyT = typename HashT<HASH>::key_t;
+  *tilemap = nullptr;
+  *n_tiles = blocks_for(src.n, kProbeTile);
+  if (t->parts <= 1 || src.gather || (int64_t)src.n < c->partition_min_probe) return HJ3D_OK;
+  if ((double)src.n * 1.04 + 8192.0 * t->parts >= 4.0e9) return HJ3D_OK;
+  Partitioned<KeyT> pr;
+  HJ_TRY((partition_local<HASH, true>(c, src, t->dir, t->parts, t->part_width, 0, &pr)));
+  uint2* tm = nullptr;
+  HJ_TRY(make_tilemap(c, pr, kProbeTile, &tm, n_tiles));
+  *tilemap = tm;
+  src = records_src(pr);
+  return HJ3D_OK;
+}
+
 template <int HASH>
 int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint32_t nb = blocks_for(src.n, kProbeTile);
+  const uint2* tilemap; uint32_t nb;
+  HJ_TRY(probe_source<HASH>(c, t, src, &tilemap, &nb));
   if (!nb) return HJ3D_OK;
+  PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Slot<KeyT>* slots = (const Slot<KeyT>*)t->slots;
-#define LAUNCH_PC(U, C, W) k_probe_chaining<HASH, U, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, t->off, slots, out, cap, c->d_ctr)
+#define LAUNCH_PC(U, C, W) k_probe_chaining<HASH, U, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, tilemap, t->off, slots, out, cap, c->d_ctr)
   if (unique) { if (cs) { if (wr) LAUNCH_PC(true, true, true); else LAUNCH_PC(true, true, false); }
                 else    { if (wr) LAUNCH_PC(true, false, true); else LAUNCH_PC(true, false, false); } }
   else        { if (cs) { if (wr) LAUNCH_PC(false, true, true); else LAUNCH_PC(false, true, false); }
@@ -295,11 +482,13 @@ int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32
 template <int HASH>
 int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint32_t nb = blocks_for(src.n, kProbeTile);
+  const uint2* tilemap; uint32_t nb;
+  HJ_TRY(probe_source<HASH>(c, t, src, &tilemap, &nb));
   if (!nb) return HJ3D_OK;
+  PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
-#define LAUNCH_PN(C, W) k_probe_nested<HASH, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, t->goff, groups, out, cap, c->d_ctr)
+#define LAUNCH_PN(C, W) k_probe_nested<HASH, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, tilemap, t->goff, groups, out, cap, c->d_ctr)
   if (cs) { if (wr) LAUNCH_PN(true, true); else LAUNCH_PN(true, false); }
   else    { if (wr) LAUNCH_PN(false, true); else LAUNCH_PN(false, false); }
 #undef LAUNCH_PN
@@ -315,9 +504,10 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   HJ_TRY(dev_alloc(c, &offsets, n + 1));
   HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
                                                 (DevStats*)nullptr, c->d_scalar)));
-  unsigned long long total = 0;
-  CUDA_TRY(cudaMemcpyAsync(&total, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long* h_tot = (unsigned long long*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h_tot, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const unsigned long long total = *h_tot;
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   if (total && (cs || wr)) {
     const uint32_t nb = (uint32_t)((total + kUnnestTile - 1) / kUnnestTile);
@@ -327,7 +517,6 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
 #undef LAUNCH_UN
     ++c->launches;
   }
-  dev_free(c, offsets);
   DevCounters* h = (DevCounters*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -338,6 +527,7 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   res->out_written = wr ? (total > cap ? cap : total) : 0;
   return HJ3D_OK;
 }
+
 
 int table_matches(hj3d_table* t, const hj3d_keyspec& ks) {
   if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
@@ -381,7 +571,7 @@ int hj3d_ctx_create(int device, hj3d_ctx** out) {
   CUDA_TRY(cudaMalloc((void**)&c->d_ctr, sizeof(DevCounters)));
   CUDA_TRY(cudaMalloc((void**)&c->d_stats, sizeof(DevStats)));
   CUDA_TRY(cudaMalloc((void**)&c->d_scalar, 4 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMallocHost(&c->h_pinned, 4096));
+  CUDA_TRY(cudaMallocHost(&c->h_pinned, 16384));
   *out = c;
   return HJ3D_OK;
 }
@@ -393,6 +583,8 @@ int hj3d_ctx_destroy(hj3d_ctx* c) {
   for (int i = 0; i < PH_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   cudaEventDestroy(c->ev_total[0]); cudaEventDestroy(c->ev_total[1]);
   cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_scalar); cudaFreeHost(c->h_pinned);
+  for (auto& k : c->arena) cudaFree(k.base);
+  cudaFree(c->hj.b); cudaFree(c->hj.p); cudaFree(c->hj.out); cudaFree(c->hj.nest); cudaFree(c->hj.l); cudaFree(c->hj.g);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return HJ3D_OK;
@@ -413,6 +605,7 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_WARP_AGGREGATE:   c->warp_aggregate = v; break;
     case HJ3D_OPT_PARTITION_BYTES:  c->partition_bytes = v; break;
     case HJ3D_OPT_PARTITION_WINDOW: c->partition_window = v > 0 ? v : c->partition_window; break;
+    case HJ3D_OPT_PARTITION_MIN_PROBE: c->partition_min_probe = v; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }
   return HJ3D_OK;
@@ -474,6 +667,7 @@ int hj3d_table_build(hj3d_ctx* c, hj3d_table* t, const void* d_tuples, uint64_t 
   if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 build tuples (row ids are 32 bit; reference cap is 2^30, main_experiment1.cc:1391)");
   HJ_TRY(check_keyspec(ks));
   CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
   begin_call(c);
   Src src = make_src(d_tuples, n, ks, nullptr);
   t->hash_id = (int)ks.hash_id; t->key_bytes = ks.key_bytes;
@@ -484,13 +678,13 @@ int hj3d_table_build(hj3d_ctx* c, hj3d_table* t, const void* d_tuples, uint64_t 
     default:                 rc = build_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src); break;
   }
   end_call(c);
-  if (rc < 0) { free_table_arrays(c, t); return rc; }
+  if (rc < 0) { clear_table(t); return rc; }
   return HJ3D_OK;
 }
 
 int hj3d_table_clear(hj3d_ctx* c, hj3d_table* t) {
   if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
-  free_table_arrays(c, t);
+  clear_table(t);
   return HJ3D_OK;
 }
 
@@ -531,6 +725,7 @@ int hj3d_table_stats(hj3d_ctx* c, hj3d_table* t, hj3d_stats* s) {
     // reference's makeStatistics is likewise called after the timed region, main_experiment1.cc:710)
     uint32_t* bitmap = nullptr;
     const uint64_t words = 1ull << 27;
+    HJ_TRY(arena_reset(c));
     HJ_TRY(dev_alloc(c, &bitmap, words));
     CUDA_TRY(cudaMemsetAsync(bitmap, 0, words * 4, c->stream));
     CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 8, c->stream));
@@ -590,12 +785,12 @@ int hj3d_probe_chaining(hj3d_ctx* c, hj3d_table* t, const void* d_probe, uint64_
   HJ_TRY(check_keyspec(ks));
   HJ_TRY(table_matches(t, ks));
   CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
   begin_call(c);
   CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
   Src src = make_src(d_probe, n, ks, d_gather);
   int rc;
   {
-    PhaseTimer pt(c, PH_PROBE);
     switch (ks.hash_id) {
       case HJ3D_HASH_MURMUR32: rc = probe_chaining_impl<HJ3D_HASH_MURMUR32>(c, t, src, unique != 0, flags, (uint2*)d_out, cap); break;
       case HJ3D_HASH_MURMUR64: rc = probe_chaining_impl<HJ3D_HASH_MURMUR64>(c, t, src, unique != 0, flags, (uint2*)d_out, cap); break;
@@ -617,12 +812,12 @@ int hj3d_probe_nested(hj3d_ctx* c, hj3d_table* t, const void* d_probe, uint64_t 
   HJ_TRY(check_keyspec(ks));
   HJ_TRY(table_matches(t, ks));
   CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
   begin_call(c);
   CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
   Src src = make_src(d_probe, n, ks, d_gather);
   int rc;
   {
-    PhaseTimer pt(c, PH_PROBE);
     switch (ks.hash_id) {
       case HJ3D_HASH_MURMUR32: rc = probe_nested_impl<HJ3D_HASH_MURMUR32>(c, t, src, flags, (uint2*)d_out, cap); break;
       case HJ3D_HASH_MURMUR64: rc = probe_nested_impl<HJ3D_HASH_MURMUR64>(c, t, src, flags, (uint2*)d_out, cap); break;
@@ -642,6 +837,7 @@ int hj3d_unnest(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_left, const uint32
   if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
   if (n && (!d_left || !d_gref)) return fail(HJ3D_ERR_INVALID, "NULL input column");
   CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
   begin_call(c);
   CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
   memset(out, 0, sizeof(*out));
@@ -695,90 +891,112 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
   if (!c || !pc) return fail(HJ3D_ERR_INVALID, "NULL argument");
   if (mode < 0 || mode > 3) return fail(HJ3D_ERR_INVALID, "mode must be 0..3");
   if (mode == 3 && !uc) return fail(HJ3D_ERR_INVALID, "unnest_out == NULL");
+  if ((nB && !h_build) || (nP && !h_probe)) return fail(HJ3D_ERR_INVALID, "NULL relation");
   CUDA_TRY(cudaSetDevice(c->device));
-  void *dB = nullptr, *dP = nullptr; uint32_t *dOut = nullptr, *dNest = nullptr, *dL = nullptr, *dG = nullptr;
-  hj3d_table* t = nullptr;
-  int rc = HJ3D_OK;
-  auto cleanup = [&]() {
-    dev_free(c, dB); dev_free(c, dP); dev_free(c, dOut); dev_free(c, dNest); dev_free(c, dL); dev_free(c, dG);
-    if (t) hj3d_table_destroy(c, t);
+  // staging buffers are ctx-owned and grow-only (the sub-calls below reset the temporary arena)
+  auto ensure = [&](void** p, size_t* have, size_t bytes) -> int {
+    if (bytes == 0) bytes = 256;
+    if (*have >= bytes) return HJ3D_OK;
+    if (*p) { cudaStreamSynchronize(c->stream); cudaFree(*p); *p = nullptr; *have = 0; }
+    HJ_TRY(raw_alloc(p, bytes));
+    *have = bytes;
+    return HJ3D_OK;
   };
-#define JH_TRY(expr) do { rc = (expr); if (rc < 0) { cleanup(); return rc; } } while (0)
-  uint8_t* b8 = nullptr; uint8_t* p8 = nullptr;
-  JH_TRY(dev_alloc(c, &b8, nB * ksB.tuple_bytes)); dB = b8;
-  JH_TRY(dev_alloc(c, &p8, nP * ksP.tuple_bytes)); dP = p8;
-  if (nB) { cudaError_t e = cudaMemcpyAsync(dB, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); } }
-  if (nP) { cudaError_t e = cudaMemcpyAsync(dP, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream); if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); } }
-  JH_TRY(hj3d_table_create(c, mode <= 1 ? HJ3D_CHAINING : HJ3D_NESTED, D, &t));
-  JH_TRY(hj3d_table_build(c, t, dB, nB, ksB));
+  auto& hj = c->hj;
+  HJ_TRY(ensure(&hj.b, &hj.cb, nB * ksB.tuple_bytes));
+  HJ_TRY(ensure(&hj.p, &hj.cp, nP * ksP.tuple_bytes));
+  if (nB) CUDA_TRY(cudaMemcpyAsync(hj.b, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (nP) CUDA_TRY(cudaMemcpyAsync(hj.p, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
+  hj3d_table* t = nullptr;
+  HJ_TRY(hj3d_table_create(c, mode <= 1 ? HJ3D_CHAINING : HJ3D_NESTED, D, &t));
+  int rc = hj3d_table_build(c, t, hj.b, nB, ksB);
+  if (rc < 0) { hj3d_table_destroy(c, t); return rc; }
   const bool want_pairs = h_out != nullptr || (flags & HJ3D_F_DEVICE_RESULT);
-  int final_rc = HJ3D_OK;
   uint64_t n_out = 0;
+  uint32_t* dOut = nullptr;
+  auto bail = [&](int code) { hj3d_table_destroy(c, t); return code; };
+  if (want_pairs) { rc = ensure(&hj.out, &hj.cout, cap * 8); if (rc < 0) return bail(rc); dOut = (uint32_t*)hj.out; }
   if (mode <= 1) {
-    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
-    JH_TRY(hj3d_probe_chaining(c, t, dP, nP, ksP, nullptr, mode == 1, flags, dOut, cap, pc));
-    final_rc = rc; n_out = pc->out_written;
+    rc = hj3d_probe_chaining(c, t, hj.p, nP, ksP, nullptr, mode == 1, flags, dOut, cap, pc);
+    if (rc < 0) return bail(rc);
+    n_out = pc->out_written;
   } else if (mode == 2) {
-    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
-    JH_TRY(hj3d_probe_nested(c, t, dP, nP, ksP, nullptr, flags, dOut, cap, pc));
-    final_rc = rc; n_out = pc->out_written;
+    rc = hj3d_probe_nested(c, t, hj.p, nP, ksP, nullptr, flags, dOut, cap, pc);
+    if (rc < 0) return bail(rc);
+    n_out = pc->out_written;
   } else {
-    JH_TRY(dev_alloc(c, &dNest, nP * 2));
-    JH_TRY(hj3d_probe_nested(c, t, dP, nP, ksP, nullptr, flags, dNest, nP, pc));
+    rc = ensure(&hj.nest, &hj.cnest, nP * 8); if (rc < 0) return bail(rc);
+    rc = hj3d_probe_nested(c, t, hj.p, nP, ksP, nullptr, flags, (uint32_t*)hj.nest, nP, pc);
+    if (rc < 0) return bail(rc);
     const uint64_t m = pc->out_written;
-    JH_TRY(dev_alloc(c, &dL, m)); JH_TRY(dev_alloc(c, &dG, m));
-    JH_TRY(hj3d_split_pairs(c, dNest, m, dL, dG));
-    if (want_pairs) JH_TRY(dev_alloc(c, &dOut, cap * 2));
-    JH_TRY(hj3d_unnest(c, t, dL, dG, m, flags, dOut, cap, uc));
-    final_rc = rc; n_out = uc->out_written;
+    rc = ensure(&hj.l, &hj.cl, m * 4); if (rc < 0) return bail(rc);
+    rc = ensure(&hj.g, &hj.cg, m * 4); if (rc < 0) return bail(rc);
+    rc = hj3d_split_pairs(c, (const uint32_t*)hj.nest, m, (uint32_t*)hj.l, (uint32_t*)hj.g);
+    if (rc < 0) return bail(rc);
+    rc = hj3d_unnest(c, t, (const uint32_t*)hj.l, (const uint32_t*)hj.g, m, flags, dOut, cap, uc);
+    if (rc < 0) return bail(rc);
+    n_out = uc->out_written;
   }
+  const int final_rc = rc;
   if (h_out && n_out) {
     cudaError_t e = cudaMemcpyAsync(h_out, dOut, n_out * 8, cudaMemcpyDeviceToHost, c->stream);
-    if (e != cudaSuccess) { cleanup(); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { hj3d_table_destroy(c, t); return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)); }
   }
-  if (st) JH_TRY(hj3d_table_stats(c, t, st));
-  cudaStreamSynchronize(c->stream);
-  cleanup();
+  if (st) { rc = hj3d_table_stats(c, t, st); if (rc < 0) return bail(rc); }
   cudaError_t e = cudaStreamSynchronize(c->stream);
+  hj3d_table_destroy(c, t);
   if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e));
-#undef JH_TRY
   return final_rc;
 }
+
+}  // extern "C"
+
+template <int HASH>
+static int partition_by_owner_t(hj3d_ctx* c, Src src, Dir d, uint32_t width, uint32_t n_owners, uint32_t rowid_base,
+                                void* d_out, uint64_t* h_counts) {
+  using KeyT = typename HashT<HASH>::key_t;
+  PhaseTimer pt(c, PH_PARTITION);
+  const PartFn pf = make_partfn(width, 0);
+  unsigned long long *counts = nullptr, *starts = nullptr, *cursor = nullptr;
+  HJ_TRY(dev_alloc(c, &counts, n_owners)); HJ_TRY(dev_alloc(c, &starts, n_owners)); HJ_TRY(dev_alloc(c, &cursor, n_owners));
+  CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)n_owners * 8, c->stream));
+  CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)n_owners * 8, c->stream));
+  const uint32_t nb = blocks_for(src.n, kPartTile);
+  if (nb) k_part_hist<HASH><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, n_owners, counts);
+  k_part_prefix<<<1, 32, 0, c->stream>>>(counts, n_owners, starts);
+  if (nb) k_part_scatter<HASH, false><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, n_owners, rowid_base, ~0ull, starts, cursor,
+                                                                         (Slot<KeyT>*)d_out);
+  c->launches += nb ? 3 : 1;
+  unsigned long long* h = (unsigned long long*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, counts, (size_t)n_owners * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < n_owners; ++i) h_counts[i] = h[i];
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+extern "C" {
 
 int hj3d_partition_by_owner(hj3d_ctx* c, const void* d_tuples, uint64_t n, hj3d_keyspec ks,
                             uint64_t D, uint32_t n_owners, uint32_t rowid_base, void* d_out, uint64_t* h_counts) {
   if (!c || !h_counts) return fail(HJ3D_ERR_INVALID, "NULL argument");
-  if (!D || D > 0xFFFFFFFFull || !n_owners || n_owners > 1024) return fail(HJ3D_ERR_INVALID, "bad num_buckets / n_owners");
+  if (!D || D > 0xFFFFFFFFull || !n_owners || n_owners > (uint32_t)kMaxParts) return fail(HJ3D_ERR_INVALID, "bad num_buckets / n_owners");
   if (n && (!d_tuples || !d_out)) return fail(HJ3D_ERR_INVALID, "NULL buffer");
   HJ_TRY(check_keyspec(ks));
   CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
   begin_call(c);
+  Src src = make_src(d_tuples, n, ks, nullptr);
+  Dir d = make_dir(D, 0, D);
+  const uint32_t width = (uint32_t)((D + n_owners - 1) / n_owners);
   int rc;
-  {
-    PhaseTimer pt(c, PH_PARTITION);
-    Src src = make_src(d_tuples, n, ks, nullptr);
-    Dir d = make_dir(D, 0, D);
-    const uint32_t width = (uint32_t)((D + n_owners - 1) / n_owners);
-    unsigned long long* d_counts = nullptr;
-    rc = dev_alloc(c, &d_counts, 2ull * n_owners);
-    if (rc == HJ3D_OK) {
-      cudaMemsetAsync(d_counts, 0, 2ull * n_owners * 8, c->stream);
-      switch (ks.hash_id) {
-        case HJ3D_HASH_MURMUR32: rc = partition_by_owner_impl<HJ3D_HASH_MURMUR32>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
-        case HJ3D_HASH_MURMUR64: rc = partition_by_owner_impl<HJ3D_HASH_MURMUR64>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
-        default:                 rc = partition_by_owner_impl<HJ3D_HASH_MURMUR64_SEXT32>(c->stream, src, d, width, n_owners, rowid_base, d_out, d_counts, &c->launches); break;
-      }
-      std::vector<unsigned long long> hc(n_owners);
-      cudaMemcpyAsync(hc.data(), d_counts, n_owners * 8ull, cudaMemcpyDeviceToHost, c->stream);
-      cudaStreamSynchronize(c->stream);
-      for (uint32_t i = 0; i < n_owners; ++i) h_counts[i] = hc[i];
-      dev_free(c, d_counts);
-    }
+  switch (ks.hash_id) {
+    case HJ3D_HASH_MURMUR32: rc = partition_by_owner_t<HJ3D_HASH_MURMUR32>(c, src, d, width, n_owners, rowid_base, d_out, h_counts); break;
+    case HJ3D_HASH_MURMUR64: rc = partition_by_owner_t<HJ3D_HASH_MURMUR64>(c, src, d, width, n_owners, rowid_base, d_out, h_counts); break;
+    default:                 rc = partition_by_owner_t<HJ3D_HASH_MURMUR64_SEXT32>(c, src, d, width, n_owners, rowid_base, d_out, h_counts); break;
   }
   end_call(c);
-  if (rc < 0) return fail(rc, "partition_by_owner failed");
-  CUDA_TRY(cudaGetLastError());
-  return HJ3D_OK;
+  return rc;
 }
 
 }  // extern "C"

@@ -50,22 +50,24 @@ __device__ __forceinline__ void commit_acc(const ProbeAcc& a, DevCounters* c, bo
 // ---- chaining probe -------------------------------------------------------------------------------
 template <int HASH, bool UNIQUE, bool CHECKSUM, bool WRITE>
 __global__ void __launch_bounds__(kProbeThreads)
-k_probe_chaining(Src s, Dir d, const uint32_t* __restrict__ off,
+k_probe_chaining(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* __restrict__ off,
                  const Slot<typename HashT<HASH>::key_t>* __restrict__ slots,
                  uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
   using KeyT = typename HashT<HASH>::key_t;
   __shared__ unsigned long long sm_scan[33];
   __shared__ unsigned long long sm_base;
-  const uint64_t base = (uint64_t)blockIdx.x * kProbeTile + threadIdx.x;
+  uint64_t t0; uint32_t tn;
+  block_tile<kProbeTile>(tilemap, s.n, t0, tn);
   ProbeAcc acc;
   KeyT     key[kProbeItems];
   uint32_t lo[kProbeItems], len[kProbeItems], nm[kProbeItems], first[kProbeItems];
   unsigned long long mine = 0;
 #pragma unroll
   for (int j = 0; j < kProbeItems; ++j) {
-    const uint64_t i = base + (uint64_t)j * kProbeThreads;
+    const uint32_t li = j * kProbeThreads + threadIdx.x;
+    const uint64_t i = t0 + li;
     lo[j] = len[j] = nm[j] = first[j] = 0; key[j] = 0;
-    if (i < s.n) {
+    if (li < tn) {
       key[j] = src_key<KeyT>(s, i);
       const uint32_t b = HashT<HASH>::bucket(key[j], d);
       if (b - d.lo < d.n_local) {                      // shard tables only own [lo, lo + n_local)
@@ -119,7 +121,7 @@ k_probe_chaining(Src s, Dir d, const uint32_t* __restrict__ off,
 #pragma unroll
     for (int j = 0; j < kProbeItems; ++j) {
       if (nm[j] == 0) continue;
-      const uint32_t left = (uint32_t)(base + (uint64_t)j * kProbeThreads);
+      const uint32_t left = src_leftid(s, t0 + j * kProbeThreads + threadIdx.x);
       if (nm[j] == 1) {
         if (CHECKSUM) { const uint64_t mx = pair_mix(left, first[j]); acc.sum += mx; acc.x ^= mx; }
         if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left, first[j]); ++pos; }
@@ -139,22 +141,24 @@ k_probe_chaining(Src s, Dir d, const uint32_t* __restrict__ off,
 // ---- nested probe ---------------------------------------------------------------------------------
 template <int HASH, bool CHECKSUM, bool WRITE>
 __global__ void __launch_bounds__(kProbeThreads)
-k_probe_nested(Src s, Dir d, const uint32_t* __restrict__ goff,
+k_probe_nested(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* __restrict__ goff,
                const Group<typename HashT<HASH>::key_t>* __restrict__ groups,
                uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
   using KeyT = typename HashT<HASH>::key_t;
   __shared__ unsigned long long sm_scan[33];
   __shared__ unsigned long long sm_base;
-  const uint64_t base = (uint64_t)blockIdx.x * kProbeTile + threadIdx.x;
+  uint64_t t0; uint32_t tn;
+  block_tile<kProbeTile>(tilemap, s.n, t0, tn);
   ProbeAcc acc;
   uint32_t gref[kProbeItems], frow[kProbeItems];
   bool     hit[kProbeItems];
   unsigned long long mine = 0;
 #pragma unroll
   for (int j = 0; j < kProbeItems; ++j) {
-    const uint64_t i = base + (uint64_t)j * kProbeThreads;
+    const uint32_t li = j * kProbeThreads + threadIdx.x;
+    const uint64_t i = t0 + li;
     hit[j] = false; gref[j] = 0; frow[j] = 0;
-    if (i >= s.n) continue;
+    if (li >= tn) continue;
     const KeyT key = src_key<KeyT>(s, i);
     const uint32_t b = HashT<HASH>::bucket(key, d);
     if (b - d.lo >= d.n_local) continue;
@@ -183,7 +187,7 @@ k_probe_nested(Src s, Dir d, const uint32_t* __restrict__ goff,
 #pragma unroll
   for (int j = 0; j < kProbeItems; ++j) {
     if (!hit[j]) continue;
-    const uint32_t left = (uint32_t)(base + (uint64_t)j * kProbeThreads);
+    const uint32_t left = src_leftid(s, t0 + j * kProbeThreads + threadIdx.x);
     if (CHECKSUM) { const uint64_t mx = pair_mix(left, frow[j]); acc.sum += mx; acc.x ^= mx; }
     if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left, gref[j]); ++pos; }
   }

@@ -192,6 +192,9 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     ctx = pkg.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    for o in args.opt:
+        k, v = o.split("=")
+        ctx.set_option(int(k), int(v))
     kind_name, build_rel, mode = PLANS[args.plan]
     kind = pkg.CHAINING if kind_name == "chaining" else pkg.NESTED
     nR, nS = 1 << args.log2_build, 1 << args.log2_probe
@@ -380,6 +383,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-checksum", dest="checksum", action="store_false")
+    ap.add_argument("--opt", action="append", default=[], help="engine option id=value (HJ3D_OPT_*), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -55,7 +55,8 @@ extern "C" {
 #define HJ3D_OPT_WARP_AGGREGATE   1 /* 0/1: warp-aggregate equal buckets before atomics (default 1)            */
 #define HJ3D_OPT_PARTITION_BYTES  2 /* table bytes above which inputs are bucket-range partitioned first;
                                        0 = never partition (default: 48 MiB)                                   */
-#define HJ3D_OPT_PARTITION_WINDOW 3 /* target table-window bytes per partition (default 16 MiB)                */
+#define HJ3D_OPT_PARTITION_WINDOW 3 /* target table-window bytes per partition (default 8 MiB)                 */
+#define HJ3D_OPT_PARTITION_MIN_PROBE 4 /* probe inputs smaller than this are probed in place (default 2^20)     */
 
 /*
  * Device-describable form of the drivers' hash / equality functors (concepts.hh:22-28,49-56):

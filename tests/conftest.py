@@ -35,9 +35,17 @@ def pkg():
     return hj3d_loader.load()
 
 
-@pytest.fixture(scope="session")
-def ctx(pkg):
+@pytest.fixture(scope="session", params=["direct", "partitioned"])
+def ctx(pkg, request):
+    """Every GPU test runs twice: on the in-place path (small tables) and with bucket-range partitioning
+    of build and probe inputs forced on (the path large tables take)."""
     import torch
     assert torch.cuda.is_available()
     # same stream as torch, so tensor fills / copies and engine kernels are ordered
-    return pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    c = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    if request.param == "partitioned":
+        c.set_option(pkg.OPT_PARTITION_BYTES, 1)
+        c.set_option(pkg.OPT_PARTITION_WINDOW, 2048)
+        c.set_option(pkg.OPT_PARTITION_MIN_PROBE, 0)
+    c.mode = request.param
+    return c
