@@ -9,7 +9,8 @@ import ctypes as C
 
 from . import capi
 from .capi import (CHAINING, F_CHECKSUM, HASH_MURMUR32, HASH_MURMUR64, HASH_MURMUR64_SEXT32, NESTED, NO_ROWID,
-                   OPT_PARTITION_BYTES, OPT_PARTITION_MIN_PROBE, OPT_PARTITION_WINDOW, OPT_WARP_AGGREGATE, Counters, Hj3dError, KeySpec,
+                   OPT_PARTITION_BYTES, OPT_PARTITION_MIN_PROBE, OPT_PARTITION_WINDOW, OPT_SMEM_CHUNK, OPT_SMEM_MIN_PROBE,
+                   OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_WARP_AGGREGATE, Counters, Hj3dError, KeySpec,
                    Stats, Timings)
 
 __all__ = ["Context", "Table", "KeySpec", "Hj3dError", "CHAINING", "NESTED", "F_CHECKSUM", "capi"]

@@ -185,6 +185,55 @@ k_group_rows(const Slot<typename HashT<HASH>::key_t>* __restrict__ slots, uint64
   }
 }
 
+// ---- physical order of short buckets ---------------------------------------------------------------
+// Buckets of 2..kOrderedMaxB entries are rewritten in the reference's own order so that the probe is a
+// plain early-exit walk (probe.cuh):
+//   chaining: chain order  [oldest, newest, .., second oldest]  (ht_chaining.hh:185-194)
+//   nested:   main chain in first-appearance order = ascending first_row (ht_nested.hh:303-308)
+// One thread per bucket; consecutive threads touch consecutive buckets = consecutive memory.
+constexpr uint32_t kOrderedMaxB = 16;   // == kOrderedMax of probe.cuh
+
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_order_slots(const uint32_t* __restrict__ off, Slot<KeyT>* __restrict__ slots, uint32_t n_buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  const uint32_t lo = off[b], n = off[b + 1] - lo;
+  if (n < 2 || n > kOrderedMaxB) return;
+  Slot<KeyT> v[kOrderedMaxB];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) if (k < n) v[k] = slots[lo + k];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) {
+    if (k >= n) break;
+    uint32_t older = 0;                                   // rank by row id = insertion order
+#pragma unroll
+    for (uint32_t m = 0; m < kOrderedMaxB; ++m) if (m < n) older += v[m].rowid < v[k].rowid;
+    const uint32_t pos = older == 0 ? 0 : n - older;      // chain position of the tuple with rank `older`
+    slots[lo + pos] = v[k];
+  }
+}
+
+template <class KeyT>
+__global__ void __launch_bounds__(256)
+k_order_groups(const uint32_t* __restrict__ goff, Group<KeyT>* __restrict__ groups, uint32_t n_buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  const uint32_t lo = goff[b], n = goff[b + 1] - lo;
+  if (n < 2 || n > kOrderedMaxB) return;
+  Group<KeyT> v[kOrderedMaxB];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) if (k < n) v[k] = groups[lo + k];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) {
+    if (k >= n) break;
+    uint32_t older = 0;
+#pragma unroll
+    for (uint32_t m = 0; m < kOrderedMaxB; ++m) if (m < n) older += v[m].first_row < v[k].first_row;
+    groups[lo + older] = v[k];
+  }
+}
+
 // ---- statistics helpers ---------------------------------------------------------------------------
 // chaining _numDistinctKeys = |{ (int)hashvalue }| (ht_chaining.hh:267,282): distinct low 32 hash bits.
 template <int HASH>

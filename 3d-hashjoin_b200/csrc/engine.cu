@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "partition.cuh"
 #include "probe.cuh"
+#include "probe_smem.cuh"
 #include "scan.cuh"
 
 using namespace hj3d;
@@ -43,6 +44,13 @@ struct hj3d_ctx {
   int64_t partition_bytes = 48ll << 20;
   int64_t partition_window = 8ll << 20;
   int64_t partition_min_probe = 1ll << 20;
+  int64_t smem_probe = 1;                    // probe through shared-memory resident fine partitions
+  int64_t smem_slice_bytes = 48 << 10;      // shared memory per block for a fine partition's table slice
+  int64_t smem_min_probe = 1ll << 16;       // smaller probe inputs use the global-memory kernels
+  int64_t smem_chunk = 1 << 16;             // probe records per work item
+  int64_t probe_threads = 256;              // shared-memory probe block size (256 | 512)
+  int64_t part_threads = 512;               // partition kernel block size (256 | 512)
+  int64_t part_rank_match = 0;              // rank by warp-private histograms + match_any instead of shared atomics
   // per-phase events of the last call
   cudaEvent_t ev[PH_COUNT][2];
   bool        ev_used[PH_COUNT];
@@ -81,6 +89,7 @@ struct hj3d_table {
   uint32_t* rows = nullptr;                // [n]               (nested)
   Buf       b_off, b_slots, b_goff, b_groups, b_rows;   // storage behind the pointers above (kept across clear())
   uint32_t  parts = 1, part_width = 0;     // bucket-range partitioning used by the build (1 = none)
+  uint32_t  fine_width = 0, fine_parts = 0; // fine partitions whose table slice fits in shared memory
   DevStats  hstats{};                      // bucket statistics captured during the build
   bool      have_stats = false;
 };
@@ -215,6 +224,7 @@ template <class KeyT> struct LoadGroupLen {
   const Group<KeyT>* groups; const uint32_t* gref; uint64_t n;
   __device__ unsigned long long operator()(uint64_t i) const { return i < n ? (unsigned long long)groups[gref[i]].len : 0ull; }
 };
+struct LoadU64 { const unsigned long long* p; __device__ unsigned long long operator()(uint64_t i) const { return p[i]; } };
 struct StoreExU64 { unsigned long long* p; __device__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const { p[i] = ex; } };
 
 void init_dev_stats_host(DevStats& s) {
@@ -224,7 +234,7 @@ void init_dev_stats_host(DevStats& s) {
 // clear(): the table becomes empty but keeps its device buffers for the next build of the repeat loop
 void clear_table(hj3d_table* t) {
   t->off = nullptr; t->slots = nullptr; t->goff = nullptr; t->groups = nullptr; t->rows = nullptr;
-  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false; t->parts = 1; t->part_width = 0;
+  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false; t->parts = 1; t->part_width = 0; t->fine_width = 0; t->fine_parts = 0;
 }
 void free_table_arrays(hj3d_ctx* c, hj3d_table* t) {
   clear_table(t);
@@ -267,8 +277,15 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
   HJ_TRY(dev_alloc(c, &out->counts, P));
   CUDA_TRY(cudaMemsetAsync(out->counts, 0, (size_t)P * 8, c->stream));
   k_part_fixed_starts<<<blocks_for(P, 256), 256, 0, c->stream>>>(P, cap, out->part_start);
-  const uint32_t nb = blocks_for(n, kPartTile);
-  if (nb) k_part_scatter<HASH, LEFTID><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, P, rowid_base, cap, out->part_start, out->counts, out->recs);
+  const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
+  const bool recs = !src.gather && src.stride == sizeof(Slot<KeyT>) && src.key_off == 0 && src.rowid_off == sizeof(KeyT) &&
+                    ((uintptr_t)src.base % sizeof(Slot<KeyT>)) == 0 && rowid_base == 0;
+  const uint32_t nb = blocks_for(n, kTile);
+  auto launch = [&](unsigned long long cap_, unsigned long long* cursor_) -> cudaError_t {
+    return launch_part_scatter<HASH, LEFTID>(c->stream, recs, (int)c->part_threads, c->part_rank_match != 0, nb, src, nullptr, d, pf,
+                                             P, P, rowid_base, cap_, out->part_start, cursor_, out->recs);
+  };
+  CUDA_TRY(launch(cap, out->counts));
   c->launches += nb ? 2 : 1;
   unsigned long long* h = (unsigned long long*)c->h_pinned;               // P <= 1024 -> 8 KB
   CUDA_TRY(cudaMemcpyAsync(h, out->counts, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -283,7 +300,7 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
     HJ_TRY(dev_alloc(c, &counts2, P));
     k_part_prefix<<<1, 32, 0, c->stream>>>(out->counts, P, out->part_start);
     CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)P * 8, c->stream));
-    k_part_scatter<HASH, LEFTID><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, P, rowid_base, ~0ull, out->part_start, counts2, out->recs);
+    CUDA_TRY(launch(~0ull, counts2));
     c->launches += 2;
   }
   CUDA_TRY(cudaGetLastError());
@@ -291,7 +308,8 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
 }
 
 template <class KeyT>
-int make_tilemap(hj3d_ctx* c, const Partitioned<KeyT>& pr, uint32_t tile, uint2** tilemap, uint32_t* n_tiles) {
+int make_tilemap(hj3d_ctx* c, const Partitioned<KeyT>& pr, uint32_t tile, uint2** tilemap, uint32_t* n_tiles,
+                 uint32_t** tile_part = nullptr) {
   uint32_t* tile_prefix = nullptr;
   HJ_TRY(dev_alloc(c, &tile_prefix, (uint64_t)pr.P + 1));
   k_tile_prefix<<<1, 1024, 0, c->stream>>>(pr.counts, pr.P, tile, tile_prefix);
@@ -300,7 +318,8 @@ int make_tilemap(hj3d_ctx* c, const Partitioned<KeyT>& pr, uint32_t tile, uint2*
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   *n_tiles = *h;
   HJ_TRY(dev_alloc(c, tilemap, (uint64_t)*n_tiles));
-  k_make_tilemap<<<pr.P, 256, 0, c->stream>>>(pr.part_start, pr.counts, tile_prefix, tile, *tilemap);
+  if (tile_part) HJ_TRY(dev_alloc(c, tile_part, (uint64_t)*n_tiles));
+  k_make_tilemap<<<pr.P, 256, 0, c->stream>>>(pr.part_start, pr.counts, tile_prefix, tile, *tilemap, tile_part ? *tile_part : nullptr);
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return HJ3D_OK;
@@ -375,6 +394,10 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
       if (agg) k_scatter<HASH, true><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off, slots);
       else     k_scatter<HASH, false><<<n_tiles, kBuildThreads, 0, c->stream>>>(bsrc, d, tilemap, t->off, slots);
       ++c->launches;
+      if (t->kind == HJ3D_CHAINING) {   // short buckets into chain order (probe.cuh walks them like algebra.hh:644-657)
+        k_order_slots<KeyT><<<blocks_for(nl, 256), 256, 0, c->stream>>>(t->off, slots, nl);
+        ++c->launches;
+      }
     }
   }
   t->n = n;
@@ -409,6 +432,10 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     }
     k_group_offsets<<<blocks_for((uint64_t)nl + 1, 256), 256, 0, c->stream>>>(t->off, gidx, nl + 1, t->goff);
     ++c->launches;
+    if (n) {   // main chains into first-appearance order (probe.cuh walks them like ht_nested.hh:371-379)
+      k_order_groups<KeyT><<<blocks_for(nl, 256), 256, 0, c->stream>>>(t->goff, groups, nl);
+      ++c->launches;
+    }
     if (n) {
       k_group_rows<HASH><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, n, rep, gstart, t->rows);
       ++c->launches;
@@ -423,6 +450,16 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   }
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaGetLastError());
+  {
+    // fine partitions: as many consecutive buckets as fit in shared memory together with their slots / groups
+    const double per_bucket = 4.0 + (t->kind == HJ3D_CHAINING ? (double)n * sizeof(Slot<KeyT>) : (double)t->n_groups * sizeof(Group<KeyT>)) / (double)(nl ? nl : 1);
+    double w = 0.85 * (double)c->smem_slice_bytes / per_bucket;
+    uint32_t fw = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
+    if (fw == 0) fw = 1;
+    if (fw < nl) { uint32_t p2 = 1; while (p2 * 2 <= fw) p2 *= 2; fw = p2; }   // power of two -> shifts instead of divisions
+    t->fine_width = fw;
+    t->fine_parts = nl ? (nl + fw - 1) / fw : 1;
+  }
   t->have_stats = true;
   t->built = true;
   return HJ3D_OK;
@@ -441,58 +478,192 @@ int fetch_counters(hj3d_ctx* c, hj3d_counters* out, uint64_t out_cap, bool wrote
   return HJ3D_OK;
 }
 
-// Probe inputs are bucket-ordered with the table's own partition function when the table was built
-// partitioned (its directory does not fit the L2 budget) and the probe side is large enough to pay
-// for the extra pass; inputs read through a gather index are probed in place.
+// ---- probe planning ---------------------------------------------------------------------------------
+// Large probe inputs are bucket-range partitioned (one or two levels) into the table's FINE partitions
+// and probed in shared memory (probe_smem.cuh); small ones use the global-memory kernels of probe.cuh,
+// optionally bucket-ordered with the build's own (coarse) partition function.
+template <class KeyT> struct ProbePlan {
+  Src             src;
+  bool            recs = false;        // src is an array of Slot<KeyT> records (one vector load per probe)
+  bool            smem = false;
+  const uint2*    work = nullptr;      // smem: work items; global: tile map (nullable)
+  const uint32_t* work_part = nullptr;
+  uint32_t        n_work = 0;
+  FineCfg         fc{};
+};
+
 template <int HASH>
-int probe_source(hj3d_ctx* c, hj3d_table* t, Src& src, const uint2** tilemap, uint32_t* n_tiles) {
+int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HASH>::key_t>* pl) {
   using KeyT = typename HashT<HASH>::key_t;
-  *tilemap = nullptr;
-  *n_tiles = blocks_for(src.n, kProbeTile);
-  if (t->parts <= 1 || src.gather || (int64_t)src.n < c->partition_min_probe) return HJ3D_OK;
-  if ((double)src.n * 1.04 + 8192.0 * t->parts >= 4.0e9) return HJ3D_OK;
+  pl->src = src;
+  pl->recs = !src.gather && src.stride == sizeof(Slot<KeyT>) && src.key_off == 0 && src.rowid_off == sizeof(KeyT) &&
+             ((uintptr_t)src.base % sizeof(Slot<KeyT>)) == 0;
+  const uint64_t n = src.n;
+  const bool can_index32 = (double)n * 1.08 + 4096.0 * (double)t->fine_parts < 4.0e9;
+  if (c->smem_probe && t->fine_width && (int64_t)n >= c->smem_min_probe && can_index32) {
+    const uint32_t F = t->fine_parts, Wf = t->fine_width, nl = t->dir.n_local;
+    const uint32_t chunk = (uint32_t)c->smem_chunk;
+    pl->smem = true;
+    {
+      const double rows_per_bucket = (t->kind == HJ3D_CHAINING ? (double)t->n * sizeof(Slot<KeyT>) : (double)t->n_groups * sizeof(Group<KeyT>)) / (double)(nl ? nl : 1);
+      const double expect = ((double)Wf + 1) * 4.0 + 32.0 + (double)Wf * rows_per_bucket;
+      uint64_t want = (uint64_t)(expect * 1.2) + 2048;
+      if (want > (uint64_t)c->smem_slice_bytes) want = (uint64_t)c->smem_slice_bytes;
+      pl->fc = FineCfg{Wf, nl, (uint32_t)(want & ~15ull)};
+    }
+    uint2* work = nullptr; uint32_t* wpart = nullptr;
+    if (F == 1) {                                    // the whole table fits: no partitioning at all
+      pl->n_work = blocks_for(n, chunk);
+      HJ_TRY(dev_alloc(c, &work, pl->n_work)); HJ_TRY(dev_alloc(c, &wpart, pl->n_work));
+      k_make_chunks<<<blocks_for(pl->n_work, 256), 256, 0, c->stream>>>(n, chunk, pl->n_work, work, wpart);
+      ++c->launches;
+      pl->work = work; pl->work_part = wpart;
+      CUDA_TRY(cudaGetLastError());
+      return HJ3D_OK;
+    }
+    Partitioned<KeyT> fine;
+    if (F <= (uint32_t)kMaxParts) {
+      HJ_TRY((partition_local<HASH, true>(c, src, t->dir, F, Wf, 0, &fine)));
+    } else {
+      // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
+      uint32_t P2 = 32;
+      while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
+      const uint64_t wc = (uint64_t)Wf * P2;
+      const uint32_t P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+      if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { pl->smem = false; goto global_path; }
+      Partitioned<KeyT> coarse;
+      HJ_TRY((partition_local<HASH, true>(c, src, t->dir, P1, (uint32_t)wc, 0, &coarse)));
+      uint2* tm = nullptr; uint32_t n_tiles = 0;
+      const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
+      HJ_TRY(make_tilemap(c, coarse, kTile, &tm, &n_tiles));
+      PhaseTimer pt(c, PH_PARTITION);
+      const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
+      const unsigned long long cap2 = n / F + n / (16ull * F) + 2048;
+      fine.P = Fall;
+      HJ_TRY(dev_alloc(c, &fine.recs, (uint64_t)Fall * cap2));
+      HJ_TRY(dev_alloc(c, &fine.part_start, Fall));
+      HJ_TRY(dev_alloc(c, &fine.counts, Fall));
+      CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
+      k_fixed_starts_u64<<<blocks_for(Fall, 256), 256, 0, c->stream>>>(Fall, cap2, fine.part_start);
+      const PartFn pf = make_partfn(Wf, t->dir.lo);
+      Src rs = records_src(coarse);
+      CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, t->dir, pf,
+                                                Fall, P2, 0, cap2, fine.part_start, fine.counts, fine.recs)));
+      unsigned long long* d_mx = c->d_scalar;
+      CUDA_TRY(cudaMemsetAsync(d_mx, 0, 16, c->stream));
+      k_max_u64<<<64, 256, 0, c->stream>>>(fine.counts, Fall, d_mx);
+      c->launches += 3;
+      unsigned long long* h = (unsigned long long*)c->h_pinned;
+      CUDA_TRY(cudaMemcpyAsync(h, d_mx, 16, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      fine.n_kept = h[1];
+      if (h[0] > cap2) {                             // skew: exact regions from the now known histogram
+        fine.fallback = true;
+        unsigned long long* counts2 = nullptr;
+        HJ_TRY(dev_alloc(c, &counts2, Fall));
+        HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{fine.part_start}, Fall, (DevStats*)nullptr, (unsigned long long*)nullptr)));
+        CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)Fall * 8, c->stream));
+        CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, t->dir, pf,
+                                                  Fall, P2, 0, ~0ull, fine.part_start, counts2, fine.recs)));
+        ++c->launches;
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    HJ_TRY(make_tilemap(c, fine, chunk, &work, &pl->n_work, &wpart));
+    pl->work = work; pl->work_part = wpart;
+    pl->src = records_src(fine);
+    pl->recs = true;
+    return HJ3D_OK;
+  }
+global_path:
+  pl->smem = false;
+  pl->work = nullptr;
+  pl->n_work = blocks_for(n, kProbeTile);
+  if (t->parts <= 1 || src.gather || (int64_t)n < c->partition_min_probe) return HJ3D_OK;
+  if ((double)n * 1.04 + 8192.0 * t->parts >= 4.0e9) return HJ3D_OK;
   Partitioned<KeyT> pr;
   HJ_TRY((partition_local<HASH, true>(c, src, t->dir, t->parts, t->part_width, 0, &pr)));
   uint2* tm = nullptr;
-  HJ_TRY(make_tilemap(c, pr, kProbeTile, &tm, n_tiles));
-  *tilemap = tm;
-  src = records_src(pr);
+  HJ_TRY(make_tilemap(c, pr, kProbeTile, &tm, &pl->n_work));
+  pl->work = tm;
+  pl->src = records_src(pr);
+  pl->recs = true;
   return HJ3D_OK;
 }
 
 template <int HASH>
 int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint2* tilemap; uint32_t nb;
-  HJ_TRY(probe_source<HASH>(c, t, src, &tilemap, &nb));
-  if (!nb) return HJ3D_OK;
+  if (!src.n) return HJ3D_OK;
+  ProbePlan<KeyT> pl;
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  if (!pl.n_work) return HJ3D_OK;
   PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Slot<KeyT>* slots = (const Slot<KeyT>*)t->slots;
-#define LAUNCH_PC(U, C, W) k_probe_chaining<HASH, U, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, tilemap, t->off, slots, out, cap, c->d_ctr)
-  if (unique) { if (cs) { if (wr) LAUNCH_PC(true, true, true); else LAUNCH_PC(true, true, false); }
-                else    { if (wr) LAUNCH_PC(true, false, true); else LAUNCH_PC(true, false, false); } }
-  else        { if (cs) { if (wr) LAUNCH_PC(false, true, true); else LAUNCH_PC(false, true, false); }
-                else    { if (wr) LAUNCH_PC(false, false, true); else LAUNCH_PC(false, false, false); } }
+  const uint32_t nb = pl.n_work;
+  if (pl.smem) {
+    const size_t sm = pl.fc.smem_bytes;
+#define LAUNCH_PS3(U, C, W, R, T) do { \
+      CUDA_TRY(cudaFuncSetAttribute(k_probe_chaining_smem<HASH, U, C, W, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      k_probe_chaining_smem<HASH, U, C, W, R, T><<<nb, T, sm, c->stream>>>(pl.src, t->dir, pl.fc, pl.work, pl.work_part, t->off, slots, out, cap, c->d_ctr); } while (0)
+#define LAUNCH_PS2(U, C, W, R) do { if (c->probe_threads == 512) LAUNCH_PS3(U, C, W, R, 512); else LAUNCH_PS3(U, C, W, R, 256); } while (0)
+#define LAUNCH_PS(U, C, W) do { if (pl.recs) LAUNCH_PS2(U, C, W, true); else LAUNCH_PS2(U, C, W, false); } while (0)
+    if (unique) { if (cs) { if (wr) LAUNCH_PS(true, true, true); else LAUNCH_PS(true, true, false); }
+                  else    { if (wr) LAUNCH_PS(true, false, true); else LAUNCH_PS(true, false, false); } }
+    else        { if (cs) { if (wr) LAUNCH_PS(false, true, true); else LAUNCH_PS(false, true, false); }
+                  else    { if (wr) LAUNCH_PS(false, false, true); else LAUNCH_PS(false, false, false); } }
+#undef LAUNCH_PS
+#undef LAUNCH_PS2
+#undef LAUNCH_PS3
+  } else {
+#define LAUNCH_PC2(U, C, W, R) k_probe_chaining<HASH, U, C, W, R><<<nb, kProbeThreads, 0, c->stream>>>(pl.src, t->dir, pl.work, t->off, slots, out, cap, c->d_ctr)
+#define LAUNCH_PC(U, C, W) do { if (pl.recs) LAUNCH_PC2(U, C, W, true); else LAUNCH_PC2(U, C, W, false); } while (0)
+    if (unique) { if (cs) { if (wr) LAUNCH_PC(true, true, true); else LAUNCH_PC(true, true, false); }
+                  else    { if (wr) LAUNCH_PC(true, false, true); else LAUNCH_PC(true, false, false); } }
+    else        { if (cs) { if (wr) LAUNCH_PC(false, true, true); else LAUNCH_PC(false, true, false); }
+                  else    { if (wr) LAUNCH_PC(false, false, true); else LAUNCH_PC(false, false, false); } }
 #undef LAUNCH_PC
+#undef LAUNCH_PC2
+  }
   ++c->launches;
+  CUDA_TRY(cudaGetLastError());
   return HJ3D_OK;
 }
 
 template <int HASH>
 int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
-  const uint2* tilemap; uint32_t nb;
-  HJ_TRY(probe_source<HASH>(c, t, src, &tilemap, &nb));
-  if (!nb) return HJ3D_OK;
+  if (!src.n) return HJ3D_OK;
+  ProbePlan<KeyT> pl;
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  if (!pl.n_work) return HJ3D_OK;
   PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
-#define LAUNCH_PN(C, W) k_probe_nested<HASH, C, W><<<nb, kProbeThreads, 0, c->stream>>>(src, t->dir, tilemap, t->goff, groups, out, cap, c->d_ctr)
-  if (cs) { if (wr) LAUNCH_PN(true, true); else LAUNCH_PN(true, false); }
-  else    { if (wr) LAUNCH_PN(false, true); else LAUNCH_PN(false, false); }
+  const uint32_t nb = pl.n_work;
+  if (pl.smem) {
+    const size_t sm = pl.fc.smem_bytes;
+#define LAUNCH_NS3(C, W, R, T) do { \
+      CUDA_TRY(cudaFuncSetAttribute(k_probe_nested_smem<HASH, C, W, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      k_probe_nested_smem<HASH, C, W, R, T><<<nb, T, sm, c->stream>>>(pl.src, t->dir, pl.fc, pl.work, pl.work_part, t->goff, groups, out, cap, c->d_ctr); } while (0)
+#define LAUNCH_NS2(C, W, R) do { if (c->probe_threads == 512) LAUNCH_NS3(C, W, R, 512); else LAUNCH_NS3(C, W, R, 256); } while (0)
+#define LAUNCH_NS(C, W) do { if (pl.recs) LAUNCH_NS2(C, W, true); else LAUNCH_NS2(C, W, false); } while (0)
+    if (cs) { if (wr) LAUNCH_NS(true, true); else LAUNCH_NS(true, false); }
+    else    { if (wr) LAUNCH_NS(false, true); else LAUNCH_NS(false, false); }
+#undef LAUNCH_NS
+#undef LAUNCH_NS2
+#undef LAUNCH_NS3
+  } else {
+#define LAUNCH_PN2(C, W, R) k_probe_nested<HASH, C, W, R><<<nb, kProbeThreads, 0, c->stream>>>(pl.src, t->dir, pl.work, t->goff, groups, out, cap, c->d_ctr)
+#define LAUNCH_PN(C, W) do { if (pl.recs) LAUNCH_PN2(C, W, true); else LAUNCH_PN2(C, W, false); } while (0)
+    if (cs) { if (wr) LAUNCH_PN(true, true); else LAUNCH_PN(true, false); }
+    else    { if (wr) LAUNCH_PN(false, true); else LAUNCH_PN(false, false); }
 #undef LAUNCH_PN
+#undef LAUNCH_PN2
+  }
   ++c->launches;
+  CUDA_TRY(cudaGetLastError());
   return HJ3D_OK;
 }
 
@@ -606,6 +777,13 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PARTITION_BYTES:  c->partition_bytes = v; break;
     case HJ3D_OPT_PARTITION_WINDOW: c->partition_window = v > 0 ? v : c->partition_window; break;
     case HJ3D_OPT_PARTITION_MIN_PROBE: c->partition_min_probe = v; break;
+    case HJ3D_OPT_SMEM_PROBE: c->smem_probe = v; break;
+    case HJ3D_OPT_SMEM_SLICE_BYTES: if (v >= 4096 && v <= (200 << 10)) c->smem_slice_bytes = v & ~15ll; break;
+    case HJ3D_OPT_SMEM_MIN_PROBE: c->smem_min_probe = v; break;
+    case HJ3D_OPT_SMEM_CHUNK: if (v >= 2048) c->smem_chunk = v; break;
+    case HJ3D_OPT_PART_THREADS: if (v == 256 || v == 512 || v == 1024) c->part_threads = v; break;
+    case HJ3D_OPT_PART_RANK_MATCH: c->part_rank_match = v != 0; break;
+    case HJ3D_OPT_PROBE_THREADS: if (v == 256 || v == 512) c->probe_threads = v; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }
   return HJ3D_OK;
@@ -962,10 +1140,12 @@ static int partition_by_owner_t(hj3d_ctx* c, Src src, Dir d, uint32_t width, uin
   CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)n_owners * 8, c->stream));
   CUDA_TRY(cudaMemsetAsync(cursor, 0, (size_t)n_owners * 8, c->stream));
   const uint32_t nb = blocks_for(src.n, kPartTile);
+  const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
+  const uint32_t nb2 = blocks_for(src.n, kTile);
   if (nb) k_part_hist<HASH><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, n_owners, counts);
   k_part_prefix<<<1, 32, 0, c->stream>>>(counts, n_owners, starts);
-  if (nb) k_part_scatter<HASH, false><<<nb, kPartThreads, 0, c->stream>>>(src, d, pf, n_owners, rowid_base, ~0ull, starts, cursor,
-                                                                         (Slot<KeyT>*)d_out);
+  CUDA_TRY((launch_part_scatter<HASH, false>(c->stream, false, (int)c->part_threads, c->part_rank_match != 0, nb2, src, nullptr, d, pf,
+                                             n_owners, n_owners, rowid_base, ~0ull, starts, cursor, (Slot<KeyT>*)d_out)));
   c->launches += nb ? 3 : 1;
   unsigned long long* h = (unsigned long long*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(h, counts, (size_t)n_owners * 8, cudaMemcpyDeviceToHost, c->stream));

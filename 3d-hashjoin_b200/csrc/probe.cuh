@@ -1,16 +1,15 @@
 // probe.cuh -- probe-side kernels: chaining probe, nested probe, deferred unnest.
 //
 // Every probe thread recomputes the counters the reference accumulates tuple-at-a-time:
-//   matches  = AlgBase::_count of the probe operator,  num_cmps = _numCmps (algebra.hh:449,658)
-// from the bucket contents alone:
-//   chaining, IsBuildKeyUnique=false : every probe into a non-empty bucket compares the whole chain (n)
-//   chaining, IsBuildKeyUnique=true  : chain order is [t0, t_{n-1}, .., t_1] (new nodes are linked right
-//                                      after the directory entry, ht_chaining.hh:189-194), so the walk
-//                                      stops at position 1 if the oldest tuple matches, else at
-//                                      n - rank + 1 of the newest matching tuple; n without a match
-//   nested                           : main chain is in first-appearance order (tail append,
-//                                      ht_nested.hh:303-308): index(key)+1 on a hit, #distinct keys on a miss
-// "oldest/newest" are decided by row id, which is the insertion order of the build strand.
+//   matches  = AlgBase::_count of the probe operator,  num_cmps = _numCmps (algebra.hh:449,658).
+// The build keeps short buckets (<= kOrderedMax entries) physically in the reference's own order:
+//   chaining : chain order [t0, t_{n-1}, .., t_1] (new nodes are linked right after the directory entry,
+//              ht_chaining.hh:189-194)  -> the probe is the same walk as algebra.hh:644-657: ++cmps per
+//              node, emit on key match, stop at the first match if IsBuildKeyUnique
+//   nested   : main chain in first-appearance order (tail append, ht_nested.hh:303-308) -> walk until the
+//              key matches: index+1 comparisons on a hit, #distinct keys on a miss (ht_nested.hh:368-381)
+// Longer buckets are left unordered and the same counters are derived from row ids ("oldest/newest" =
+// smallest/largest row id = insertion order of the build strand).
 //
 // Results are written with block-aggregated allocation: one atomicAdd on the output cursor per
 // block tile, pairs of a tile land contiguously (coalesced 8-byte stores).
@@ -23,6 +22,7 @@ namespace hj3d {
 constexpr int kProbeThreads = 256;
 constexpr int kProbeItems   = 4;
 constexpr int kProbeTile    = kProbeThreads * kProbeItems;
+constexpr uint32_t kOrderedMax = 16;   // buckets up to this length are stored in chain / first-appearance order
 
 struct ProbeAcc {
   unsigned long long matches = 0, cmps = 0, sum = 0, x = 0;
@@ -47,8 +47,179 @@ __device__ __forceinline__ void commit_acc(const ProbeAcc& a, DevCounters* c, bo
   }
 }
 
-// ---- chaining probe -------------------------------------------------------------------------------
-template <int HASH, bool UNIQUE, bool CHECKSUM, bool WRITE>
+// (key, left id) of probe tuple i.  RECS: the input is an array of Slot<KeyT> records (partitioned or
+// exchanged data) and is read with one vector load; otherwise a strided row-store tuple.
+template <class KeyT, bool RECS>
+__device__ __forceinline__ void load_probe(const Src& s, uint64_t i, KeyT& key, uint32_t& left) {
+  if (RECS) {
+    const Slot<KeyT> r = reinterpret_cast<const Slot<KeyT>*>(s.base)[i];
+    key = r.key; left = r.rowid;
+  } else {
+    key = src_key<KeyT>(s, i);
+    left = src_leftid(s, i);
+  }
+}
+
+// ---- one tile of chaining probes ----------------------------------------------------------------------
+// offp[b] .. offp[b+1] (minus slot_base) delimit bucket b's slots in slotp; both may live in shared or
+// global memory (the address space is known at every inlined call site).
+template <class KeyT, bool UNIQUE, bool CHECKSUM, bool WRITE, bool RECS, int THREADS, int ITEMS, int HASH>
+__device__ __forceinline__ void probe_chaining_tile(const Src& s, const Dir& d, uint64_t t0, uint32_t tn,
+                                                    uint32_t bucket_base, uint32_t n_buckets,
+                                                    const uint32_t* offp, uint32_t slot_base, const Slot<KeyT>* slotp,
+                                                    uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr,
+                                                    ProbeAcc& acc, unsigned long long* sm_scan, unsigned long long* sm_base) {
+  KeyT     key[ITEMS];
+  uint32_t left[ITEMS], lo[ITEMS], len[ITEMS], nm[ITEMS], first[ITEMS];
+  unsigned long long mine = 0;   // a tile's matches can exceed 2^32 when many probes hit one hot key
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t li = j * THREADS + threadIdx.x;
+    lo[j] = len[j] = nm[j] = first[j] = left[j] = 0; key[j] = 0;
+    if (li < tn) load_probe<KeyT, RECS>(s, t0 + li, key[j], left[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t li = j * THREADS + threadIdx.x;
+    if (li < tn) {
+      const uint32_t b = HashT<HASH>::bucket(key[j], d) - bucket_base;
+      if (b < n_buckets) { const uint32_t o0 = offp[b]; lo[j] = o0 - slot_base; len[j] = offp[b + 1] - o0; }
+    }
+  }
+  uint32_t cmps = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t n = len[j];
+    if (n == 0) continue;                               // empty bucket: no comparison (algebra.hh:640-643)
+    const Slot<KeyT>* sp = slotp + lo[j];
+    if (!UNIQUE) {
+      uint32_t m = 0, f = 0;
+      for (uint32_t k = 0; k < n; ++k) {
+        const Slot<KeyT> sl = sp[k];
+        if (sl.key == key[j]) { if (m == 0) f = sl.rowid; ++m; }
+      }
+      nm[j] = m; first[j] = f;
+      cmps += n;                                        // whole chain is walked (algebra.hh:644-657)
+    } else if (n <= kOrderedMax) {
+      uint32_t k = 0;                                   // chain order: stop at the first match (algebra.hh:653-655)
+      for (; k < n; ++k) {
+        const Slot<KeyT> sl = sp[k];
+        if (sl.key == key[j]) { nm[j] = 1; first[j] = sl.rowid; break; }
+      }
+      cmps += k < n ? k + 1 : n;
+    } else {
+      // unordered long bucket: first match in chain order [oldest, newest, .., second oldest] from row ids
+      uint32_t min_row = 0xFFFFFFFFu, best = 0; bool any = false, min_is_match = false;
+      for (uint32_t k = 0; k < n; ++k) {
+        const Slot<KeyT> sl = sp[k];
+        const bool hit = sl.key == key[j];
+        if (sl.rowid < min_row) { min_row = sl.rowid; min_is_match = hit; }
+        if (hit && (!any || sl.rowid > best)) { best = sl.rowid; any = true; }
+      }
+      if (!any) { cmps += n; }
+      else if (min_is_match) { cmps += 1; nm[j] = 1; first[j] = min_row; }
+      else {
+        uint32_t rank = 0;                              // #tuples of the bucket inserted before `best`
+        for (uint32_t k = 0; k < n; ++k) rank += sp[k].rowid < best;
+        cmps += n - rank + 1; nm[j] = 1; first[j] = best;
+      }
+    }
+    mine += nm[j];
+  }
+  acc.matches += mine;
+  acc.cmps += cmps;
+  // ---- output allocation: block exclusive scan + one atomic per tile
+  unsigned long long pos = 0;
+  if (WRITE) {
+    unsigned long long tot;
+    const unsigned long long ex = block_exscan(mine, sm_scan, &tot);
+    if (threadIdx.x == 0) *sm_base = tot ? atomicAdd(&ctr->out_cursor, tot) : 0ull;
+    __syncthreads();
+    pos = *sm_base + ex;
+  }
+  if (WRITE || CHECKSUM) {
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      if (nm[j] == 0) continue;
+      if (nm[j] == 1) {
+        if (CHECKSUM) { const uint64_t mx = pair_mix(left[j], first[j]); acc.sum += mx; acc.x ^= mx; }
+        if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left[j], first[j]); ++pos; }
+      } else {
+        const Slot<KeyT>* sp = slotp + lo[j];
+        for (uint32_t k = 0; k < len[j]; ++k) {
+          const Slot<KeyT> sl = sp[k];
+          if (sl.key != key[j]) continue;
+          if (CHECKSUM) { const uint64_t mx = pair_mix(left[j], sl.rowid); acc.sum += mx; acc.x ^= mx; }
+          if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left[j], sl.rowid); ++pos; }
+        }
+      }
+    }
+  }
+}
+
+// ---- one tile of nested probes ------------------------------------------------------------------------
+template <class KeyT, bool CHECKSUM, bool WRITE, bool RECS, int THREADS, int ITEMS, int HASH>
+__device__ __forceinline__ void probe_nested_tile(const Src& s, const Dir& d, uint64_t t0, uint32_t tn,
+                                                  uint32_t bucket_base, uint32_t n_buckets,
+                                                  const uint32_t* offp, uint32_t group_base, const Group<KeyT>* grp,
+                                                  uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr,
+                                                  ProbeAcc& acc, unsigned long long* sm_scan, unsigned long long* sm_base) {
+  uint32_t left[ITEMS], gref[ITEMS], frow[ITEMS];
+  bool     hit[ITEMS];
+  uint32_t mine = 0, cmps = 0;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const uint32_t li = j * THREADS + threadIdx.x;
+    hit[j] = false; gref[j] = 0; frow[j] = 0; left[j] = 0;
+    if (li >= tn) continue;
+    KeyT key;
+    load_probe<KeyT, RECS>(s, t0 + li, key, left[j]);
+    const uint32_t b = HashT<HASH>::bucket(key, d) - bucket_base;
+    if (b >= n_buckets) continue;
+    const uint32_t o0 = offp[b], dk = offp[b + 1] - o0;
+    if (dk == 0) continue;                               // empty bucket: {nullptr, 0} (ht_nested.hh:372)
+    const Group<KeyT>* gp = grp + (o0 - group_base);
+    if (dk <= kOrderedMax) {
+      uint32_t k = 0;                                    // first-appearance order: the walk of ht_nested.hh:371-379
+      for (; k < dk; ++k) {
+        const Group<KeyT> g = gp[k];
+        if (g.key == key) { hit[j] = true; gref[j] = o0 + k; frow[j] = g.first_row; break; }
+      }
+      cmps += k < dk ? k + 1 : dk;
+    } else {
+      uint32_t my_first = 0, my_g = 0; bool found = false;
+      for (uint32_t k = 0; k < dk && !found; ++k) {
+        const Group<KeyT> g = gp[k];
+        if (g.key == key) { found = true; my_first = g.first_row; my_g = o0 + k; }
+      }
+      if (!found) { cmps += dk; continue; }
+      uint32_t before = 0;                               // groups whose first tuple was inserted earlier
+      for (uint32_t k = 0; k < dk; ++k) before += gp[k].first_row < my_first;
+      cmps += before + 1;
+      hit[j] = true; gref[j] = my_g; frow[j] = my_first;
+    }
+    mine += hit[j];
+  }
+  acc.matches += mine;
+  acc.cmps += cmps;
+  unsigned long long pos = 0;
+  if (WRITE) {
+    unsigned long long tot;
+    const unsigned long long ex = block_exscan((unsigned long long)mine, sm_scan, &tot);
+    if (threadIdx.x == 0) *sm_base = tot ? atomicAdd(&ctr->out_cursor, tot) : 0ull;
+    __syncthreads();
+    pos = *sm_base + ex;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    if (!hit[j]) continue;
+    if (CHECKSUM) { const uint64_t mx = pair_mix(left[j], frow[j]); acc.sum += mx; acc.x ^= mx; }
+    if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left[j], gref[j]); ++pos; }
+  }
+}
+
+// ---- global-memory lookups (small inputs / fallback) ---------------------------------------------------
+template <int HASH, bool UNIQUE, bool CHECKSUM, bool WRITE, bool RECS>
 __global__ void __launch_bounds__(kProbeThreads)
 k_probe_chaining(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* __restrict__ off,
                  const Slot<typename HashT<HASH>::key_t>* __restrict__ slots,
@@ -59,87 +230,12 @@ k_probe_chaining(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t
   uint64_t t0; uint32_t tn;
   block_tile<kProbeTile>(tilemap, s.n, t0, tn);
   ProbeAcc acc;
-  KeyT     key[kProbeItems];
-  uint32_t lo[kProbeItems], len[kProbeItems], nm[kProbeItems], first[kProbeItems];
-  unsigned long long mine = 0;
-#pragma unroll
-  for (int j = 0; j < kProbeItems; ++j) {
-    const uint32_t li = j * kProbeThreads + threadIdx.x;
-    const uint64_t i = t0 + li;
-    lo[j] = len[j] = nm[j] = first[j] = 0; key[j] = 0;
-    if (li < tn) {
-      key[j] = src_key<KeyT>(s, i);
-      const uint32_t b = HashT<HASH>::bucket(key[j], d);
-      if (b - d.lo < d.n_local) {                      // shard tables only own [lo, lo + n_local)
-        lo[j] = off[b - d.lo];
-        len[j] = off[b - d.lo + 1] - lo[j];
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kProbeItems; ++j) {
-    const uint32_t n = len[j];
-    if (n == 0) continue;                               // empty bucket: no comparison (algebra.hh:640-643)
-    if (!UNIQUE) {
-      uint32_t m = 0, f = 0;
-      for (uint32_t k = 0; k < n; ++k) {
-        const Slot<KeyT> sl = slots[lo[j] + k];
-        if (sl.key == key[j]) { if (m == 0) f = sl.rowid; ++m; }
-      }
-      nm[j] = m; first[j] = f;
-      acc.cmps += n;                                    // whole chain is walked (algebra.hh:644-657)
-    } else {
-      // first match in chain order [oldest, newest, .., second oldest]
-      uint32_t min_row = 0xFFFFFFFFu, min_match = 0, best = 0; bool any = false, min_is_match = false;
-      for (uint32_t k = 0; k < n; ++k) {
-        const Slot<KeyT> sl = slots[lo[j] + k];
-        const bool hit = sl.key == key[j];
-        if (sl.rowid < min_row) { min_row = sl.rowid; min_is_match = hit; min_match = sl.rowid; }
-        if (hit && (!any || sl.rowid > best)) { best = sl.rowid; any = true; }
-      }
-      if (!any) { acc.cmps += n; }
-      else if (min_is_match) { acc.cmps += 1; nm[j] = 1; first[j] = min_match; }
-      else {
-        uint32_t rank = 0;                              // #tuples of the bucket inserted before `best`
-        for (uint32_t k = 0; k < n; ++k) rank += slots[lo[j] + k].rowid < best;
-        acc.cmps += n - rank + 1; nm[j] = 1; first[j] = best;
-      }
-    }
-    mine += nm[j];
-  }
-  acc.matches = mine;
-  // ---- output allocation: block exclusive scan + one atomic per tile
-  unsigned long long pos = 0;
-  if (WRITE) {
-    unsigned long long tot;
-    pos = block_exscan(mine, sm_scan, &tot);
-    if (threadIdx.x == 0) sm_base = tot ? atomicAdd(&ctr->out_cursor, tot) : 0ull;
-    __syncthreads();
-    pos += sm_base;
-  }
-  if (WRITE || CHECKSUM) {
-#pragma unroll
-    for (int j = 0; j < kProbeItems; ++j) {
-      if (nm[j] == 0) continue;
-      const uint32_t left = src_leftid(s, t0 + j * kProbeThreads + threadIdx.x);
-      if (nm[j] == 1) {
-        if (CHECKSUM) { const uint64_t mx = pair_mix(left, first[j]); acc.sum += mx; acc.x ^= mx; }
-        if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left, first[j]); ++pos; }
-      } else {
-        for (uint32_t k = 0; k < len[j]; ++k) {
-          const Slot<KeyT> sl = slots[lo[j] + k];
-          if (sl.key != key[j]) continue;
-          if (CHECKSUM) { const uint64_t mx = pair_mix(left, sl.rowid); acc.sum += mx; acc.x ^= mx; }
-          if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left, sl.rowid); ++pos; }
-        }
-      }
-    }
-  }
+  probe_chaining_tile<KeyT, UNIQUE, CHECKSUM, WRITE, RECS, kProbeThreads, kProbeItems, HASH>(
+      s, d, t0, tn, d.lo, d.n_local, off, 0u, slots, out, out_cap, ctr, acc, sm_scan, &sm_base);
   commit_acc(acc, ctr, CHECKSUM);
 }
 
-// ---- nested probe ---------------------------------------------------------------------------------
-template <int HASH, bool CHECKSUM, bool WRITE>
+template <int HASH, bool CHECKSUM, bool WRITE, bool RECS>
 __global__ void __launch_bounds__(kProbeThreads)
 k_probe_nested(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* __restrict__ goff,
                const Group<typename HashT<HASH>::key_t>* __restrict__ groups,
@@ -150,47 +246,8 @@ k_probe_nested(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* 
   uint64_t t0; uint32_t tn;
   block_tile<kProbeTile>(tilemap, s.n, t0, tn);
   ProbeAcc acc;
-  uint32_t gref[kProbeItems], frow[kProbeItems];
-  bool     hit[kProbeItems];
-  unsigned long long mine = 0;
-#pragma unroll
-  for (int j = 0; j < kProbeItems; ++j) {
-    const uint32_t li = j * kProbeThreads + threadIdx.x;
-    const uint64_t i = t0 + li;
-    hit[j] = false; gref[j] = 0; frow[j] = 0;
-    if (li >= tn) continue;
-    const KeyT key = src_key<KeyT>(s, i);
-    const uint32_t b = HashT<HASH>::bucket(key, d);
-    if (b - d.lo >= d.n_local) continue;
-    const uint32_t glo = goff[b - d.lo], dk = goff[b - d.lo + 1] - glo;
-    if (dk == 0) continue;                               // empty bucket: {nullptr, 0} (ht_nested.hh:372)
-    uint32_t my_first = 0, my_g = 0; bool found = false;
-    for (uint32_t k = 0; k < dk && !found; ++k) {
-      const Group<KeyT> g = groups[glo + k];
-      if (g.key == key) { found = true; my_first = g.first_row; my_g = glo + k; }
-    }
-    if (!found) { acc.cmps += dk; continue; }            // walked the whole main chain (ht_nested.hh:378-381)
-    uint32_t before = 0;                                 // groups whose first tuple was inserted earlier
-    for (uint32_t k = 0; k < dk; ++k) before += groups[glo + k].first_row < my_first;
-    acc.cmps += before + 1;
-    hit[j] = true; gref[j] = my_g; frow[j] = my_first; ++mine;
-  }
-  acc.matches = mine;
-  unsigned long long pos = 0;
-  if (WRITE) {
-    unsigned long long tot;
-    pos = block_exscan(mine, sm_scan, &tot);
-    if (threadIdx.x == 0) sm_base = tot ? atomicAdd(&ctr->out_cursor, tot) : 0ull;
-    __syncthreads();
-    pos += sm_base;
-  }
-#pragma unroll
-  for (int j = 0; j < kProbeItems; ++j) {
-    if (!hit[j]) continue;
-    const uint32_t left = src_leftid(s, t0 + j * kProbeThreads + threadIdx.x);
-    if (CHECKSUM) { const uint64_t mx = pair_mix(left, frow[j]); acc.sum += mx; acc.x ^= mx; }
-    if (WRITE) { if (pos < out_cap) out[pos] = make_uint2(left, gref[j]); ++pos; }
-  }
+  probe_nested_tile<KeyT, CHECKSUM, WRITE, RECS, kProbeThreads, kProbeItems, HASH>(
+      s, d, t0, tn, d.lo, d.n_local, goff, 0u, groups, out, out_cap, ctr, acc, sm_scan, &sm_base);
   commit_acc(acc, ctr, CHECKSUM);
 }
 

@@ -57,6 +57,13 @@ extern "C" {
                                        0 = never partition (default: 48 MiB)                                   */
 #define HJ3D_OPT_PARTITION_WINDOW 3 /* target table-window bytes per partition (default 8 MiB)                 */
 #define HJ3D_OPT_PARTITION_MIN_PROBE 4 /* probe inputs smaller than this are probed in place (default 2^20)     */
+#define HJ3D_OPT_SMEM_PROBE       5 /* 0/1: probe through shared-memory resident fine partitions (default 1)    */
+#define HJ3D_OPT_SMEM_SLICE_BYTES 6 /* shared memory per block for a fine partition's table slice (default 48 KiB) */
+#define HJ3D_OPT_SMEM_MIN_PROBE   7 /* probe inputs smaller than this use the global-memory kernels (default 2^16) */
+#define HJ3D_OPT_SMEM_CHUNK       8 /* probe records per work item of the shared-memory probe (default 2^16)     */
+#define HJ3D_OPT_PART_THREADS     9 /* partition kernel block size: 256, 512 or 1024 (default 512)               */
+#define HJ3D_OPT_PROBE_THREADS   11 /* shared-memory probe block size: 256 or 512 (default 256)                  */
+#define HJ3D_OPT_PART_RANK_MATCH 10 /* 0: rank by shared-memory atomics (default), 1: warp-private histograms + match_any (slower on B200) */
 
 /*
  * Device-describable form of the drivers' hash / equality functors (concepts.hh:22-28,49-56):

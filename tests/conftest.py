@@ -35,17 +35,29 @@ def pkg():
     return hj3d_loader.load()
 
 
-@pytest.fixture(scope="session", params=["direct", "partitioned"])
+@pytest.fixture(scope="session", params=["direct", "partitioned", "smem"])
 def ctx(pkg, request):
-    """Every GPU test runs twice: on the in-place path (small tables) and with bucket-range partitioning
-    of build and probe inputs forced on (the path large tables take)."""
+    """Every GPU test runs on all three probe paths: in place with global-memory lookups (small inputs),
+    bucket-range partitioned with L2-window lookups, and partitioned into fine partitions probed in
+    shared memory (what large inputs take), the latter two forced on at test sizes."""
     import torch
     assert torch.cuda.is_available()
     # same stream as torch, so tensor fills / copies and engine kernels are ordered
     c = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    if request.param == "direct":
+        c.set_option(pkg.OPT_SMEM_PROBE, 0)
     if request.param == "partitioned":
+        c.set_option(pkg.OPT_SMEM_PROBE, 0)
         c.set_option(pkg.OPT_PARTITION_BYTES, 1)
         c.set_option(pkg.OPT_PARTITION_WINDOW, 2048)
         c.set_option(pkg.OPT_PARTITION_MIN_PROBE, 0)
+        c.set_option(pkg.capi.OPT_PART_THREADS, 256)       # also cover the other partition kernel variants
+        c.set_option(pkg.capi.OPT_PART_RANK_MATCH, 1)
+    if request.param == "smem":
+        c.set_option(pkg.OPT_PARTITION_BYTES, 1)
+        c.set_option(pkg.OPT_PARTITION_WINDOW, 65536)
+        c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0)
+        c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
+        c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
     c.mode = request.param
     return c

@@ -79,11 +79,28 @@ def test_zipf_heavy_hitter(pkg, ctx, oracle):
         assert_plan_equal(g, o, f"zipf/mode{mode}")
 
 
+def test_two_level_fine_partitioning(pkg, ctx, oracle):
+    """a directory wide enough that the probe input needs two partition levels to reach shared-memory
+    sized fine partitions (> 1024 fine partitions at the test's 4 KiB slices); skewed variant overflows
+    the fixed-capacity fine regions and takes the exact fallback."""
+    rng = np.random.default_rng(23)
+    nB, nP, D = 300000, 500000, 300007
+    B = np.zeros((nB, 2), np.uint32); B[:, 0] = np.arange(nB); B[:, 1] = rng.integers(0, 1 << 30, nB)
+    P = np.zeros((nP, 2), np.uint32); P[:, 0] = B[rng.integers(0, nB, nP), 1]
+    for mode in (1, 0, 3):
+        g, o = both(pkg, ctx, oracle, mode, B, (8, 4, 4, 0), D, P, (8, 0, 4, 0))
+        assert_plan_equal(g, o, f"two-level/mode{mode}")
+    P[: nP // 2, 0] = B[7, 1]                                   # half of the probes hit one key
+    for mode in (0, 3):
+        g, o = both(pkg, ctx, oracle, mode, B, (8, 4, 4, 0), D, P, (8, 0, 4, 0))
+        assert_plan_equal(g, o, f"two-level-skew/mode{mode}")
+
+
 def test_partition_overflow_falls_back_to_exact_regions(pkg, ctx, oracle):
     """90% of the rows hash into one bucket range: the fixed-capacity regions of the single-pass
     partitioner overflow and the exact two-step layout is used instead -- same results."""
-    if ctx.mode != "partitioned":
-        pytest.skip("partitioned path only")
+    if ctx.mode == "direct":
+        pytest.skip("partitioned paths only")
     rng = np.random.default_rng(17)
     nB, nP, D = 400000, 300000, 64
     hot = 12345
@@ -91,13 +108,14 @@ def test_partition_overflow_falls_back_to_exact_regions(pkg, ctx, oracle):
     B[:, 1] = np.where(rng.random(nB) < 0.9, hot, rng.integers(0, 1 << 20, nB)).astype(np.uint32)
     P = np.zeros((nP, 2), np.uint32)
     P[:, 0] = np.where(rng.random(nP) < 0.0001, hot, rng.integers(0, 1 << 20, nP)).astype(np.uint32)
+    old_window = 65536 if ctx.mode == "smem" else 2048
     ctx.set_option(pkg.OPT_PARTITION_WINDOW, 1 << 20)          # few, large partitions
     try:
         for mode in (0, 3):
             g, o = both(pkg, ctx, oracle, mode, B, (8, 4, 4, 0), D, P, (8, 0, 4, 0))
             assert_plan_equal(g, o, f"overflow/mode{mode}")
     finally:
-        ctx.set_option(pkg.OPT_PARTITION_WINDOW, 2048)
+        ctx.set_option(pkg.OPT_PARTITION_WINDOW, old_window)
 
 
 def test_gather_indirection(pkg, ctx, oracle):
