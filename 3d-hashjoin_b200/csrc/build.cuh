@@ -19,6 +19,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace hj3d {
 
@@ -193,6 +194,49 @@ k_group_rows(const Slot<typename HashT<HASH>::key_t>* __restrict__ slots, uint64
 // One thread per bucket; consecutive threads touch consecutive buckets = consecutive memory.
 constexpr uint32_t kOrderedMaxB = 16;   // == kOrderedMax of probe.cuh
 
+
+// In-place reorder of one short bucket (2 <= n <= kOrderedMaxB) at base[0..n).
+// CHAIN = true : chain order of HtChaining1 = [oldest, newest, .., second oldest]   (key = rowid)
+// CHAIN = false: ascending by `first_row` (first-appearance order of HtNested1's main chain)
+template <class T> __device__ __forceinline__ uint32_t order_key(const T& v);
+template <> __device__ __forceinline__ uint32_t order_key(const Slot<uint32_t>& v) { return v.rowid; }
+template <> __device__ __forceinline__ uint32_t order_key(const Slot<uint64_t>& v) { return v.rowid; }
+template <> __device__ __forceinline__ uint32_t order_key(const Group<uint32_t>& v) { return v.first_row; }
+template <> __device__ __forceinline__ uint32_t order_key(const Group<uint64_t>& v) { return v.first_row; }
+
+template <class T, bool CHAIN>
+__device__ __forceinline__ void order_short_bucket(T* base, uint32_t n) {
+  if (n <= 4) {   // 93% of the multi-entry buckets of a load-factor-1 table: 4-element sorting network
+    T v0 = base[0], v1 = base[1], v2 = n > 2 ? base[2] : v1, v3 = n > 3 ? base[3] : v1;
+    uint32_t k0 = order_key(v0), k1 = order_key(v1), k2 = n > 2 ? order_key(v2) : 0xFFFFFFFFu, k3 = n > 3 ? order_key(v3) : 0xFFFFFFFFu;
+#define HJ_CSWAP(a, b, ka, kb) do { if (kb < ka) { T t_ = a; a = b; b = t_; uint32_t u_ = ka; ka = kb; kb = u_; } } while (0)
+    HJ_CSWAP(v0, v1, k0, k1); HJ_CSWAP(v2, v3, k2, k3); HJ_CSWAP(v0, v2, k0, k2); HJ_CSWAP(v1, v3, k1, k3); HJ_CSWAP(v1, v2, k1, k2);
+#undef HJ_CSWAP
+    if (CHAIN) {      // ascending a<b<c<d  ->  [a, d, c, b]
+      base[0] = v0;
+      if (n == 2) base[1] = v1;
+      else if (n == 3) { base[1] = v2; base[2] = v1; }
+      else { base[1] = v3; base[2] = v2; base[3] = v1; }
+    } else {
+      base[0] = v0; base[1] = v1;
+      if (n > 2) base[2] = v2;
+      if (n > 3) base[3] = v3;
+    }
+    return;
+  }
+  T v[kOrderedMaxB];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) if (k < n) v[k] = base[k];
+#pragma unroll
+  for (uint32_t k = 0; k < kOrderedMaxB; ++k) {
+    if (k >= n) break;
+    uint32_t older = 0;                                   // rank by row id = insertion order
+#pragma unroll
+    for (uint32_t m = 0; m < kOrderedMaxB; ++m) if (m < n) older += order_key(v[m]) < order_key(v[k]);
+    base[CHAIN ? (older == 0 ? 0 : n - older) : older] = v[k];
+  }
+}
+
 template <class KeyT>
 __global__ void __launch_bounds__(256)
 k_order_slots(const uint32_t* __restrict__ off, Slot<KeyT>* __restrict__ slots, uint32_t n_buckets) {
@@ -200,18 +244,7 @@ k_order_slots(const uint32_t* __restrict__ off, Slot<KeyT>* __restrict__ slots, 
   if (b >= n_buckets) return;
   const uint32_t lo = off[b], n = off[b + 1] - lo;
   if (n < 2 || n > kOrderedMaxB) return;
-  Slot<KeyT> v[kOrderedMaxB];
-#pragma unroll
-  for (uint32_t k = 0; k < kOrderedMaxB; ++k) if (k < n) v[k] = slots[lo + k];
-#pragma unroll
-  for (uint32_t k = 0; k < kOrderedMaxB; ++k) {
-    if (k >= n) break;
-    uint32_t older = 0;                                   // rank by row id = insertion order
-#pragma unroll
-    for (uint32_t m = 0; m < kOrderedMaxB; ++m) if (m < n) older += v[m].rowid < v[k].rowid;
-    const uint32_t pos = older == 0 ? 0 : n - older;      // chain position of the tuple with rank `older`
-    slots[lo + pos] = v[k];
-  }
+  order_short_bucket<Slot<KeyT>, true>(slots + lo, n);
 }
 
 template <class KeyT>
@@ -221,17 +254,113 @@ k_order_groups(const uint32_t* __restrict__ goff, Group<KeyT>* __restrict__ grou
   if (b >= n_buckets) return;
   const uint32_t lo = goff[b], n = goff[b + 1] - lo;
   if (n < 2 || n > kOrderedMaxB) return;
-  Group<KeyT> v[kOrderedMaxB];
+  order_short_bucket<Group<KeyT>, false>(groups + lo, n);
+}
+
+// ---- fine-partition build (chaining): one block builds one bucket range completely in shared memory ----
+// Input: the build records of fine partition f (bucket range [f*width, (f+1)*width)), contiguous at
+// recs[part_start[f] .. +counts[f]).  The block histograms them over its `width` buckets (one shared
+// atomic per record, which also yields the record's rank inside its bucket), scans the histogram,
+// places the records at off[b] + rank, rewrites short buckets in chain order (k_order_slots) and
+// streams the finished directory words and slots to global memory with coalesced stores.  The bucket
+// statistics of makeStatistics are reduced on the way.  base[f] = number of build records in
+// partitions < f.  A partition with more than `cap_recs` records sets *overflow and is skipped (the
+// caller then rebuilds with the global-memory kernels).
+constexpr int kFineBuildThreads = 512;
+constexpr int kFineBuildItems   = 12;
+
+template <int HASH>
+__global__ void __launch_bounds__(kFineBuildThreads)
+k_build_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
+             const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
+             const unsigned long long* __restrict__ base, Dir d, uint32_t width, uint32_t n_fine, uint32_t cap_recs,
+             uint32_t* __restrict__ off, Slot<typename HashT<HASH>::key_t>* __restrict__ slots,
+             DevStats* stats, uint32_t* overflow) {
+  using KeyT = typename HashT<HASH>::key_t;
+  using SlotT = Slot<KeyT>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* sm_off = reinterpret_cast<uint32_t*>(smem_raw);                 // [width + 1] counts -> exclusive offsets
+  SlotT*    sm_slots = reinterpret_cast<SlotT*>(smem_raw + (((width + 1) * 4 + 15) & ~15u));
+  __shared__ uint32_t sm_scan[33];
+  __shared__ unsigned long long sm_red[160];
+
+  const uint32_t f = blockIdx.x;
+  const uint32_t blo = f * width;
+  const uint32_t bhi = (blo + width < d.n_local) ? blo + width : d.n_local;
+  const uint32_t nbk = bhi - blo;
+  const unsigned long long cnt64 = f < n_fine ? counts[f] : 0ull;
+  if (cnt64 > cap_recs) { if (threadIdx.x == 0) atomicExch(overflow, 1u); return; }
+  const uint32_t cnt = (uint32_t)cnt64;
+  const uint32_t gbase = (uint32_t)base[f];
+  const SlotT* in = recs + (f < n_fine ? part_start[f] : 0ull);
+  for (uint32_t b = threadIdx.x; b <= nbk; b += kFineBuildThreads) sm_off[b] = 0;
+  // ---- load this partition's records (registers) and histogram them
+  KeyT     key[kFineBuildItems];
+  uint32_t rid[kFineBuildItems], br[kFineBuildItems];      // br = (local bucket << 14) | rank ... rank < 2^14, bucket < 2^18
 #pragma unroll
-  for (uint32_t k = 0; k < kOrderedMaxB; ++k) if (k < n) v[k] = groups[lo + k];
-#pragma unroll
-  for (uint32_t k = 0; k < kOrderedMaxB; ++k) {
-    if (k >= n) break;
-    uint32_t older = 0;
-#pragma unroll
-    for (uint32_t m = 0; m < kOrderedMaxB; ++m) if (m < n) older += v[m].first_row < v[k].first_row;
-    groups[lo + older] = v[k];
+  for (int j = 0; j < kFineBuildItems; ++j) {
+    const uint32_t li = j * kFineBuildThreads + threadIdx.x;
+    key[j] = 0; rid[j] = 0;
+    if (li < cnt) { const SlotT r = in[li]; key[j] = r.key; rid[j] = r.rowid; }
   }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kFineBuildItems; ++j) {
+    const uint32_t li = j * kFineBuildThreads + threadIdx.x;
+    br[j] = 0xFFFFFFFFu;
+    if (li < cnt) {
+      const uint32_t b = HashT<HASH>::bucket(key[j], d) - d.lo - blo;
+      br[j] = (b << 14) | atomicAdd(&sm_off[b], 1u);
+    }
+  }
+  __syncthreads();
+  // ---- statistics over the bucket lengths + exclusive scan (in place)
+  {
+    DevAgg all{~0ull, 0, 0, 0, 0}, ne{~0ull, 0, 0, 0, 0};
+    unsigned long long empty = 0;
+    constexpr uint32_t PER = 8;                              // width <= 4096 = 512 threads x 8
+    const uint32_t a = threadIdx.x * PER;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) {
+      v[k] = 0;
+      if (a + k < nbk) {
+        v[k] = sm_off[a + k];
+        stats_step(all, v[k]);
+        if (v[k]) stats_step(ne, v[k]); else ++empty;
+      }
+      sum += v[k];
+    }
+    uint32_t tot;
+    uint32_t ex = block_exscan(sum, sm_scan, &tot);
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) { if (a + k < nbk) sm_off[a + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) sm_off[nbk] = cnt;
+    agg_commit(all, &stats->all, sm_red);
+    agg_commit(ne, &stats->nonempty, sm_red);
+    empty = warp_sum(empty);
+    if (lane_id() == 0 && empty) atomicAdd(&stats->empty, empty);
+  }
+  __syncthreads();
+  // ---- place the records
+#pragma unroll
+  for (int j = 0; j < kFineBuildItems; ++j) {
+    if (br[j] == 0xFFFFFFFFu) continue;
+    SlotT r; r.key = key[j]; r.rowid = rid[j];
+    sm_slots[sm_off[br[j] >> 14] + (br[j] & 0x3FFFu)] = r;
+  }
+  __syncthreads();
+  // ---- short buckets into chain order [oldest, newest, .., second oldest] (ht_chaining.hh:185-194)
+  for (uint32_t b = threadIdx.x; b < nbk; b += kFineBuildThreads) {
+    const uint32_t lo = sm_off[b], n = sm_off[b + 1] - lo;
+    if (n < 2 || n > kOrderedMaxB) continue;
+    order_short_bucket<SlotT, true>(sm_slots + lo, n);
+  }
+  __syncthreads();
+  // ---- stream out: directory words (global offsets) and slots
+  for (uint32_t b = threadIdx.x; b < nbk; b += kFineBuildThreads) off[blo + b] = gbase + sm_off[b];
+  if (bhi == d.n_local && threadIdx.x == 0) off[d.n_local] = gbase + cnt;
+  for (uint32_t i = threadIdx.x; i < cnt; i += kFineBuildThreads) slots[gbase + i] = sm_slots[i];
 }
 
 // ---- statistics helpers ---------------------------------------------------------------------------

@@ -44,6 +44,8 @@ struct hj3d_ctx {
   int64_t partition_bytes = 48ll << 20;
   int64_t partition_window = 8ll << 20;
   int64_t partition_min_probe = 1ll << 20;
+  int64_t smem_build = 1;                    // build chaining tables range-by-range in shared memory
+  int64_t smem_build_bytes = 64 << 10;       // shared memory budget of one build range
   int64_t smem_probe = 1;                    // probe through shared-memory resident fine partitions
   int64_t smem_slice_bytes = 48 << 10;      // shared memory per block for a fine partition's table slice
   int64_t smem_min_probe = 1ll << 16;       // smaller probe inputs use the global-memory kernels
@@ -331,7 +333,135 @@ template <class KeyT> Src records_src(const Partitioned<KeyT>& pr) {
   return s;
 }
 
+// Partition `src` into the F fine bucket ranges of width Wf (one level if F <= 1024, else coarse
+// partitions of P2 consecutive fine ones first).  *ok = false: not representable (caller falls back).
+template <int HASH, bool LEFTID>
+int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
+                   Partitioned<typename HashT<HASH>::key_t>* fine_out, bool* ok) {
+  using KeyT = typename HashT<HASH>::key_t;
+  Partitioned<KeyT>& fine = *fine_out;
+  const uint64_t n = src.n;
+  const uint32_t nl = dir.n_local;
+  *ok = true;
+  if (F <= (uint32_t)kMaxParts) {
+    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, F, Wf, 0, &fine)));
+    return HJ3D_OK;
+  }
+  // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
+  uint32_t P2 = 32;
+  while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
+  const uint64_t wc = (uint64_t)Wf * P2;
+  const uint32_t P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+  if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { *ok = false; return HJ3D_OK; }
+  Partitioned<KeyT> coarse;
+  HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, P1, (uint32_t)wc, 0, &coarse)));
+  uint2* tm = nullptr; uint32_t n_tiles = 0;
+  const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
+  HJ_TRY(make_tilemap(c, coarse, kTile, &tm, &n_tiles));
+  PhaseTimer pt(c, PH_PARTITION);
+  const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
+  const unsigned long long cap2 = n / F + n / (16ull * F) + 2048;
+  fine.P = Fall;
+  HJ_TRY(dev_alloc(c, &fine.recs, (uint64_t)Fall * cap2));
+  HJ_TRY(dev_alloc(c, &fine.part_start, Fall));
+  HJ_TRY(dev_alloc(c, &fine.counts, Fall));
+  CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
+  k_fixed_starts_u64<<<blocks_for(Fall, 256), 256, 0, c->stream>>>(Fall, cap2, fine.part_start);
+  const PartFn pf = make_partfn(Wf, dir.lo);
+  Src rs = records_src(coarse);
+  // the ids stored in the coarse records are final (left ids / row ids): level 2 just carries them (LEFTID + RECS)
+  CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, dir, pf,
+                                            Fall, P2, 0, cap2, fine.part_start, fine.counts, fine.recs)));
+  unsigned long long* d_mx = c->d_scalar;
+  CUDA_TRY(cudaMemsetAsync(d_mx, 0, 16, c->stream));
+  k_max_u64<<<64, 256, 0, c->stream>>>(fine.counts, Fall, d_mx);
+  c->launches += 3;
+  unsigned long long* h = (unsigned long long*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, d_mx, 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  fine.n_kept = h[1];
+  if (h[0] > cap2) {                             // skew: exact regions from the now known histogram
+    fine.fallback = true;
+    unsigned long long* counts2 = nullptr;
+    HJ_TRY(dev_alloc(c, &counts2, Fall));
+    HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{fine.part_start}, Fall, (DevStats*)nullptr, (unsigned long long*)nullptr)));
+    CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)Fall * 8, c->stream));
+    CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, dir, pf,
+                                              Fall, P2, 0, ~0ull, fine.part_start, counts2, fine.recs)));
+    ++c->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+// fine partitions: as many consecutive buckets as fit in shared memory together with their slots / groups
+inline void set_fine_width(hj3d_ctx* c, hj3d_table* t, double payload_bytes_total) {
+  const uint32_t nl = t->dir.n_local;
+  const double per_bucket = 4.0 + payload_bytes_total / (double)(nl ? nl : 1);
+  double w = 0.85 * (double)c->smem_slice_bytes / per_bucket;
+  uint32_t fw = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
+  if (fw == 0) fw = 1;
+  if (fw > 4096) fw = 4096;                                                   // k_build_fine scans 8 buckets per thread
+  if (fw < nl) { uint32_t p2 = 1; while (p2 * 2 <= fw) p2 *= 2; fw = p2; }   // power of two -> shifts instead of divisions
+  t->fine_width = fw;
+  t->fine_parts = nl ? (nl + fw - 1) / fw : 1;
+}
+
 // ---- build ----------------------------------------------------------------------------------------
+// Chaining tables over large inputs: partition the build side into fine bucket ranges and let one block
+// build each range in shared memory (k_build_fine).  Returns *done = false when a range does not fit
+// (skewed / heavily duplicated keys): the caller then uses the global-memory kernels below.
+template <int HASH>
+int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT<HASH>::key_t>* slots, bool* done) {
+  using KeyT = typename HashT<HASH>::key_t;
+  *done = false;
+  const uint64_t n = src.n;
+  const uint32_t nl = t->dir.n_local;
+  // bucket ranges of the build kernel: as wide as ~6K build records / 4096 buckets allow
+  uint32_t Wf;
+  {
+    const double per_bucket = 4.0 + (double)n * sizeof(Slot<KeyT>) / (double)(nl ? nl : 1);
+    double w = 0.85 * (double)c->smem_build_bytes / per_bucket;
+    Wf = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
+    if (Wf > 4096) Wf = 4096;
+    if (Wf < nl) { uint32_t p2 = 1; while (p2 * 2 <= Wf) p2 *= 2; Wf = p2; }
+  }
+  const uint32_t F = nl ? (nl + Wf - 1) / Wf : 1;
+  if (!c->smem_build || (int64_t)n < c->smem_min_probe || F < 2) return HJ3D_OK;
+  if ((double)n * 1.08 + 4096.0 * (double)F >= 4.0e9) return HJ3D_OK;
+  Partitioned<KeyT> fine;
+  bool ok = false;
+  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok)));
+  if (!ok) return HJ3D_OK;
+  PhaseTimer pt(c, PH_SCATTER);
+  unsigned long long* base = nullptr;
+  HJ_TRY(dev_alloc(c, &base, (uint64_t)fine.P + 1));
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{base}, fine.P, (DevStats*)nullptr, (unsigned long long*)nullptr)));
+  const uint32_t off_bytes = ((Wf + 1) * 4 + 15) & ~15u;
+  uint32_t cap_recs = kFineBuildThreads * kFineBuildItems;
+  const uint32_t smem_max = 160u << 10;
+  if (off_bytes + (uint64_t)cap_recs * sizeof(Slot<KeyT>) > smem_max) cap_recs = (smem_max - off_bytes) / sizeof(Slot<KeyT>);
+  // right-size: expected records per range + 25% + 512
+  const uint64_t expect = n / F + n / (4ull * F) + 512;
+  if (expect < cap_recs) cap_recs = (uint32_t)expect;
+  const size_t sm = off_bytes + (size_t)cap_recs * sizeof(Slot<KeyT>);
+  uint32_t* d_flag = (uint32_t*)(c->d_scalar + 2);
+  CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, c->stream));
+  CUDA_TRY(cudaFuncSetAttribute(k_build_fine<HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  // ranges past fine.P (two-level rounding never creates them; one-level has exactly F) -> grid = F
+  k_build_fine<HASH><<<F, kFineBuildThreads, sm, c->stream>>>(fine.recs, fine.part_start, fine.counts, base, t->dir, Wf, fine.P,
+                                                              cap_recs, t->off, slots, c->d_stats, d_flag);
+  ++c->launches;
+  uint32_t* h = (uint32_t*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (*h) return HJ3D_OK;                                   // some range overflowed shared memory
+  (void)nl;
+  *done = true;
+  return HJ3D_OK;
+}
+
 template <int HASH>
 int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   using KeyT = typename HashT<HASH>::key_t;
@@ -344,6 +474,20 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   if (t->kind == HJ3D_CHAINING) HJ_TRY(buf_ensure(c, t->b_slots, &slots, n));
   else                          HJ_TRY(dev_alloc(c, &slots, n));          // nested: only needed during the build
   t->slots = slots;
+  if (t->kind == HJ3D_CHAINING) {
+    set_fine_width(c, t, (double)n * sizeof(Slot<KeyT>));
+    DevStats hs0; init_dev_stats_host(hs0);
+    CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs0, sizeof(hs0), cudaMemcpyHostToDevice, c->stream));
+    bool done = false;
+    HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done));
+    if (done) {
+      t->n = n; t->parts = 1; t->part_width = nl ? nl : 1;
+      CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaGetLastError());
+      t->have_stats = true; t->built = true;
+      return HJ3D_OK;
+    }
+  }
 
   // bucket-order the input first when the directory + slots do not fit the L2 window budget
   const uint64_t table_bytes = (uint64_t)nl * 4 + n * sizeof(Slot<KeyT>);
@@ -450,16 +594,7 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   }
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaGetLastError());
-  {
-    // fine partitions: as many consecutive buckets as fit in shared memory together with their slots / groups
-    const double per_bucket = 4.0 + (t->kind == HJ3D_CHAINING ? (double)n * sizeof(Slot<KeyT>) : (double)t->n_groups * sizeof(Group<KeyT>)) / (double)(nl ? nl : 1);
-    double w = 0.85 * (double)c->smem_slice_bytes / per_bucket;
-    uint32_t fw = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
-    if (fw == 0) fw = 1;
-    if (fw < nl) { uint32_t p2 = 1; while (p2 * 2 <= fw) p2 *= 2; fw = p2; }   // power of two -> shifts instead of divisions
-    t->fine_width = fw;
-    t->fine_parts = nl ? (nl + fw - 1) / fw : 1;
-  }
+  if (t->kind == HJ3D_NESTED) set_fine_width(c, t, (double)t->n_groups * sizeof(Group<KeyT>));
   t->have_stats = true;
   t->built = true;
   return HJ3D_OK;
@@ -522,53 +657,9 @@ int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HAS
       return HJ3D_OK;
     }
     Partitioned<KeyT> fine;
-    if (F <= (uint32_t)kMaxParts) {
-      HJ_TRY((partition_local<HASH, true>(c, src, t->dir, F, Wf, 0, &fine)));
-    } else {
-      // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
-      uint32_t P2 = 32;
-      while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
-      const uint64_t wc = (uint64_t)Wf * P2;
-      const uint32_t P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
-      if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { pl->smem = false; goto global_path; }
-      Partitioned<KeyT> coarse;
-      HJ_TRY((partition_local<HASH, true>(c, src, t->dir, P1, (uint32_t)wc, 0, &coarse)));
-      uint2* tm = nullptr; uint32_t n_tiles = 0;
-      const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
-      HJ_TRY(make_tilemap(c, coarse, kTile, &tm, &n_tiles));
-      PhaseTimer pt(c, PH_PARTITION);
-      const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
-      const unsigned long long cap2 = n / F + n / (16ull * F) + 2048;
-      fine.P = Fall;
-      HJ_TRY(dev_alloc(c, &fine.recs, (uint64_t)Fall * cap2));
-      HJ_TRY(dev_alloc(c, &fine.part_start, Fall));
-      HJ_TRY(dev_alloc(c, &fine.counts, Fall));
-      CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
-      k_fixed_starts_u64<<<blocks_for(Fall, 256), 256, 0, c->stream>>>(Fall, cap2, fine.part_start);
-      const PartFn pf = make_partfn(Wf, t->dir.lo);
-      Src rs = records_src(coarse);
-      CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, t->dir, pf,
-                                                Fall, P2, 0, cap2, fine.part_start, fine.counts, fine.recs)));
-      unsigned long long* d_mx = c->d_scalar;
-      CUDA_TRY(cudaMemsetAsync(d_mx, 0, 16, c->stream));
-      k_max_u64<<<64, 256, 0, c->stream>>>(fine.counts, Fall, d_mx);
-      c->launches += 3;
-      unsigned long long* h = (unsigned long long*)c->h_pinned;
-      CUDA_TRY(cudaMemcpyAsync(h, d_mx, 16, cudaMemcpyDeviceToHost, c->stream));
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
-      fine.n_kept = h[1];
-      if (h[0] > cap2) {                             // skew: exact regions from the now known histogram
-        fine.fallback = true;
-        unsigned long long* counts2 = nullptr;
-        HJ_TRY(dev_alloc(c, &counts2, Fall));
-        HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{fine.part_start}, Fall, (DevStats*)nullptr, (unsigned long long*)nullptr)));
-        CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)Fall * 8, c->stream));
-        CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, t->dir, pf,
-                                                  Fall, P2, 0, ~0ull, fine.part_start, counts2, fine.recs)));
-        ++c->launches;
-      }
-      CUDA_TRY(cudaGetLastError());
-    }
+    bool ok = false;
+    HJ_TRY((partition_fine<HASH, true>(c, src, t->dir, Wf, F, &fine, &ok)));
+    if (!ok) { pl->smem = false; goto global_path; }
     HJ_TRY(make_tilemap(c, fine, chunk, &work, &pl->n_work, &wpart));
     pl->work = work; pl->work_part = wpart;
     pl->src = records_src(fine);
@@ -778,6 +869,8 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PARTITION_WINDOW: c->partition_window = v > 0 ? v : c->partition_window; break;
     case HJ3D_OPT_PARTITION_MIN_PROBE: c->partition_min_probe = v; break;
     case HJ3D_OPT_SMEM_PROBE: c->smem_probe = v; break;
+    case HJ3D_OPT_SMEM_BUILD: c->smem_build = v; break;
+    case HJ3D_OPT_SMEM_BUILD_BYTES: if (v >= 2048 && v <= (160 << 10)) c->smem_build_bytes = v; break;
     case HJ3D_OPT_SMEM_SLICE_BYTES: if (v >= 4096 && v <= (200 << 10)) c->smem_slice_bytes = v & ~15ll; break;
     case HJ3D_OPT_SMEM_MIN_PROBE: c->smem_min_probe = v; break;
     case HJ3D_OPT_SMEM_CHUNK: if (v >= 2048) c->smem_chunk = v; break;

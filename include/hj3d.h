@@ -62,6 +62,8 @@ extern "C" {
 #define HJ3D_OPT_SMEM_MIN_PROBE   7 /* probe inputs smaller than this use the global-memory kernels (default 2^16) */
 #define HJ3D_OPT_SMEM_CHUNK       8 /* probe records per work item of the shared-memory probe (default 2^16)     */
 #define HJ3D_OPT_PART_THREADS     9 /* partition kernel block size: 256, 512 or 1024 (default 512)               */
+#define HJ3D_OPT_SMEM_BUILD      12 /* 0/1: build chaining tables range-by-range in shared memory (default 1)    */
+#define HJ3D_OPT_SMEM_BUILD_BYTES 13 /* shared memory budget of one build range (default 64 KiB)               */
 #define HJ3D_OPT_PROBE_THREADS   11 /* shared-memory probe block size: 256 or 512 (default 256)                  */
 #define HJ3D_OPT_PART_RANK_MATCH 10 /* 0: rank by shared-memory atomics (default), 1: warp-private histograms + match_any (slower on B200) */
 

@@ -46,8 +46,10 @@ def ctx(pkg, request):
     c = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
     if request.param == "direct":
         c.set_option(pkg.OPT_SMEM_PROBE, 0)
+        c.set_option(pkg.capi.OPT_SMEM_BUILD, 0)
     if request.param == "partitioned":
         c.set_option(pkg.OPT_SMEM_PROBE, 0)
+        c.set_option(pkg.capi.OPT_SMEM_BUILD, 0)
         c.set_option(pkg.OPT_PARTITION_BYTES, 1)
         c.set_option(pkg.OPT_PARTITION_WINDOW, 2048)
         c.set_option(pkg.OPT_PARTITION_MIN_PROBE, 0)
@@ -58,6 +60,7 @@ def ctx(pkg, request):
         c.set_option(pkg.OPT_PARTITION_WINDOW, 65536)
         c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0)
         c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
+        c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096)
         c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
     c.mode = request.param
     return c
