@@ -30,6 +30,7 @@ SYMBOLS = [
     "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
+    "hj3d_mem_alloc", "hj3d_mem_free", "hj3d_memcpy_h2d", "hj3d_memcpy_d2h", "hj3d_iota_u32",
 ]
 
 
@@ -112,6 +113,11 @@ def load():
     L.hj3d_partition_by_owner.argtypes = [vp, vp, u64, KeySpec, u64, u32, u32, vp, C.POINTER(u64)]
     L.hj3d_owner_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_stats_merge.argtypes = [C.POINTER(Stats), u32, C.POINTER(Stats)]
+    L.hj3d_mem_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.hj3d_mem_free.argtypes = [vp, vp]
+    L.hj3d_memcpy_h2d.argtypes = [vp, vp, vp, u64]
+    L.hj3d_memcpy_d2h.argtypes = [vp, vp, vp, u64]
+    L.hj3d_iota_u32.argtypes = [vp, vp, u64, u32]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:

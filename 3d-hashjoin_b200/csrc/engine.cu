@@ -905,6 +905,42 @@ int hj3d_ctx_timings(hj3d_ctx* c, hj3d_timings* out) {
   return HJ3D_OK;
 }
 
+int hj3d_mem_alloc(hj3d_ctx* c, uint64_t bytes, void** out) {
+  if (!c || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return raw_alloc(out, bytes ? bytes : 256);
+}
+int hj3d_mem_free(hj3d_ctx* c, void* p) {
+  if (!c) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!p) return HJ3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(p));
+  return HJ3D_OK;
+}
+int hj3d_memcpy_h2d(hj3d_ctx* c, void* d, const void* h, uint64_t bytes) {
+  if (!c || (bytes && (!d || !h))) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  return HJ3D_OK;
+}
+int hj3d_memcpy_d2h(hj3d_ctx* c, void* h, const void* d, uint64_t bytes) {
+  if (!c || (bytes && (!d || !h))) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return HJ3D_OK;
+}
+int hj3d_iota_u32(hj3d_ctx* c, uint32_t* d, uint64_t n, uint32_t first) {
+  if (!c || (n && !d)) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!n) return HJ3D_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  k_iota_u32<<<blocks_for(n, 256), 256, 0, c->stream>>>(d, n, first);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
 int hj3d_owner_range(uint64_t D, uint32_t n_owners, uint32_t owner, uint64_t* lo, uint64_t* hi) {
   if (!D || !n_owners || owner >= n_owners || !lo || !hi) return fail(HJ3D_ERR_INVALID, "bad owner range arguments");
   const uint64_t w = (D + n_owners - 1) / n_owners;

@@ -320,6 +320,10 @@ __global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* _
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[idx[i]];
 }
+__global__ void k_iota_u32(uint32_t* __restrict__ dst, uint64_t n, uint32_t first) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = first + (uint32_t)i;
+}
 __global__ void k_split_pairs(const uint2* __restrict__ pairs, uint64_t n, uint32_t* __restrict__ l, uint32_t* __restrict__ r) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const uint2 p = pairs[i]; l[i] = p.x; r[i] = p.y; }

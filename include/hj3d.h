@@ -127,6 +127,17 @@ int hj3d_ctx_set_option(hj3d_ctx* ctx, int option, int64_t value);
 int hj3d_ctx_sync(hj3d_ctx* ctx);
 int hj3d_ctx_timings(hj3d_ctx* ctx, hj3d_timings* out);
 
+/* ---- device memory helpers (so that host code above the ABI needs no CUDA headers) -----------
+ * The reference keeps relations in std::vector<tuple_t> (RelationRS, algebra.hh:98-106); the shims
+ * copy them to device memory they own through these calls.  Copies are ordered on the ctx's stream;
+ * d2h blocks until the data has arrived. */
+int hj3d_mem_alloc(hj3d_ctx* ctx, uint64_t bytes, void** d_out);
+int hj3d_mem_free(hj3d_ctx* ctx, void* d_ptr);
+int hj3d_memcpy_h2d(hj3d_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes);
+int hj3d_memcpy_d2h(hj3d_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes);
+/* d_dst[i] = first + i  (identity column, e.g. the `left` of a second deferred unnest) */
+int hj3d_iota_u32(hj3d_ctx* ctx, uint32_t* d_dst, uint64_t n, uint32_t first);
+
 /* ---- build side ----------------------------------------------------------------------------
  * hj3d_table_create  <- HtChaining1 / HtNested1 constructors via AlgHashJoinBuild(aHashDirSize, ..)
  *                       / AlgNestJoinBuild(aHashDirSize, .., ..)   (algebra.hh:566-569, 372-380;
