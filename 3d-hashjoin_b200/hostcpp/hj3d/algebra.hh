@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <deque>
 #include <functional>
 #include <iomanip>
 #include <iostream>
@@ -254,10 +255,13 @@ template <class Hashfun>
 struct ProbeInput {
   using input_t = typename Hashfun::input_t;
   TupleSeq<input_t> seq;
+  std::deque<std::remove_const_t<input_t>> owned;   // tuples pushed one at a time may be the producer's scratch tuple
   DevBuf dbuf;
   std::vector<std::remove_const_t<input_t>> staging;
   hj3d_keyspec ks{};
-  void clear() { seq.clear(); }
+  void clear() { seq.clear(); owned.clear(); }
+  // step(): the pointee is only valid during the call (algebra.hh:455-457,650-652 reuse one _outputTuple) -> keep a copy
+  void push_copy(input_t* t) { owned.push_back(*t); seq.push(&owned.back()); }
   // returns the device pointer of the tuples whose key the functor hashes
   const void* upload() {
     if constexpr (derefs_to_base<Hashfun>) {
@@ -382,7 +386,7 @@ class AlgNestJoinProbe : public AlgBase {
     AlgNestJoinProbe(consumer_t* aConsumer, build_t* aBuildOperator)
       : AlgBase("AlgNestJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {}
     inline void init(globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
-    inline void step(input_t* aProbeTuple, [[maybe_unused]] globstat_t* g) { _in.seq.push(aProbeTuple); }
+    inline void step(input_t* aProbeTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aProbeTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
     inline void fin(globstat_t* g) {
       using namespace hj3d;
@@ -460,7 +464,7 @@ class AlgHashJoinProbe : public AlgBase {
     inline AlgHashJoinProbe(consumer_t* aConsumer, build_t* aBuildOperator)
       : AlgBase("AlgHashJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {}
     inline void init([[maybe_unused]] globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
-    inline void step(input_t* aTuple, [[maybe_unused]] globstat_t* g) { _in.seq.push(aTuple); }
+    inline void step(input_t* aTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
     inline void fin(globstat_t* g) {
       using namespace hj3d;
