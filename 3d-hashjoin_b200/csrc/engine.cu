@@ -14,6 +14,7 @@
 #include "partition.cuh"
 #include "probe.cuh"
 #include "probe_smem.cuh"
+#include "probe_cluster.cuh"
 #include "scan.cuh"
 
 using namespace hj3d;
@@ -53,6 +54,12 @@ struct hj3d_ctx {
   int64_t probe_threads = 256;              // shared-memory probe block size (256 | 512)
   int64_t part_threads = 512;               // partition kernel block size (256 | 512)
   int64_t part_rank_match = 0;              // rank by warp-private histograms + match_any instead of shared atomics
+  int64_t cluster_probe = 0;                // probe coarse partitions with thread-block clusters (probe_cluster.cuh); experimental:
+                                            // correct on every parity case, not yet faster than the two-level path
+  int64_t cluster_min_probe = 1ll << 22;    // smaller probe inputs use the other paths
+  int64_t cluster_min_parts = 64;           // coarse partitions needed to keep every cluster busy
+  int64_t cluster_slice_bytes = 0;          // > 0: cap on the slice's shared memory (tests)
+  int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // per-phase events of the last call
   cudaEvent_t ev[PH_COUNT][2];
   bool        ev_used[PH_COUNT];
@@ -682,10 +689,86 @@ global_path:
   return HJ3D_OK;
 }
 
+// ---- cluster probe (probe_cluster.cuh): one partition pass of fan-out <= 1024, C SMs share a partition's table slice ----
+template <int HASH, int KIND, bool CS, bool WR>
+int launch_probe_cluster(hj3d_ctx* c, hj3d_table* t, const Partitioned<typename HashT<HASH>::key_t>& pr, ClusterCfg cc,
+                         uint2* out, uint64_t cap, bool* ok) {
+  using KeyT = typename HashT<HASH>::key_t;
+  constexpr int C = kClC;
+  auto kfn = k_probe_cluster<HASH, KIND, CS, WR>;
+  const size_t sm = 2 * (size_t)ClTile<KeyT>::kTile * sizeof(Slot<KeyT>) + cc.slice_bytes;
+  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(C * (c->sm_count / C)), 1, 1);
+  cfg.blockDim = dim3(kClThreads, 1, 1);
+  cfg.dynamicSmemBytes = sm;
+  cfg.stream = c->stream;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n_clusters = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, kfn, &cfg);
+  if (e != cudaSuccess || n_clusters < 1) { cudaGetLastError(); *ok = false; return HJ3D_OK; }
+  if (getenv("HJ3D_DEBUG")) fprintf(stderr, "[hj3d] cluster probe: C=%d max active clusters=%d parts=%u sub_shift=%u slice_bytes=%u smem=%zu\n",
+                                    C, n_clusters, cc.n_parts, cc.sub_shift, cc.slice_bytes, sm);
+  if ((uint32_t)n_clusters > cc.n_parts) n_clusters = (int)cc.n_parts;
+  cfg.gridDim = dim3((unsigned)(C * n_clusters), 1, 1);
+  const void* rows = KIND == 0 ? (const void*)t->slots : (const void*)t->groups;
+  const uint32_t* off = KIND == 0 ? t->off : t->goff;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, (const Slot<KeyT>*)pr.recs, (const unsigned long long*)pr.part_start,
+                              (const unsigned long long*)pr.counts, t->dir, cc, off, rows, out, (unsigned long long)cap, c->d_ctr));
+  ++c->launches;
+  *ok = true;
+  return HJ3D_OK;
+}
+
+// Geometry: the widest power-of-two bucket range per CTA whose slice fits shared memory, narrowed until the
+// table splits into enough coarse partitions to keep all clusters busy.  *ok = false: use the other paths.
+template <int HASH, int KIND>
+int probe_cluster_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* ok) {
+  using KeyT = typename HashT<HASH>::key_t;
+  using RowT = typename std::conditional<KIND == 0, Slot<KeyT>, Group<KeyT>>::type;
+  constexpr int C = kClC;
+  *ok = false;
+  const uint64_t n = src.n;
+  const uint32_t nl = t->dir.n_local;
+  if (!c->cluster_probe || (int64_t)n < c->cluster_min_probe || nl < 2) return HJ3D_OK;
+  if ((double)n * 1.04 + 8192.0 * kMaxParts >= 4.0e9) return HJ3D_OK;
+  const uint64_t n_rows = KIND == 0 ? t->n : t->n_groups;
+  const size_t staging = 2 * (size_t)ClTile<KeyT>::kTile * sizeof(Slot<KeyT>);
+  int64_t budget = (int64_t)c->smem_optin - 3072 - (int64_t)staging;
+  if (budget < 16384) return HJ3D_OK;
+  if (c->cluster_slice_bytes > 0 && c->cluster_slice_bytes < budget) budget = c->cluster_slice_bytes;
+  const double per_bucket = 2.0 + (double)n_rows * sizeof(RowT) / (double)nl;
+  uint32_t shift = 0;
+  while (shift < 15 && (double)(2u << shift) * per_bucket * 1.04 + 256.0 <= (double)budget) ++shift;   // 2^shift buckets fit
+  while (shift > 0 && ((uint64_t)nl >> (shift + 3)) < (uint64_t)c->cluster_min_parts) --shift;         // enough partitions
+  const uint64_t width = (uint64_t)C << shift;
+  const uint64_t P = ((uint64_t)nl + width - 1) / width;
+  if (P > (uint64_t)kMaxParts || P < (uint64_t)c->cluster_min_parts) return HJ3D_OK;
+  Partitioned<KeyT> pr;
+  HJ_TRY((partition_local<HASH, true>(c, src, t->dir, (uint32_t)P, (uint32_t)width, 0, &pr)));
+  PhaseTimer pt(c, PH_PROBE);
+  ClusterCfg cc{shift, nl, (uint32_t)P, (uint32_t)(budget & ~15ll)};
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  if (cs) { if (wr) HJ_TRY((launch_probe_cluster<HASH, KIND, true, true>(c, t, pr, cc, out, cap, ok)));
+            else    HJ_TRY((launch_probe_cluster<HASH, KIND, true, false>(c, t, pr, cc, out, cap, ok))); }
+  else    { if (wr) HJ_TRY((launch_probe_cluster<HASH, KIND, false, true>(c, t, pr, cc, out, cap, ok)));
+            else    HJ_TRY((launch_probe_cluster<HASH, KIND, false, false>(c, t, pr, cc, out, cap, ok))); }
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
 template <int HASH>
 int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
   if (!src.n) return HJ3D_OK;
+  if (!src.gather && unique) {              // at most one result per probe tuple
+    bool ok = false;
+    HJ_TRY((probe_cluster_impl<HASH, 0>(c, t, src, flags, out, cap, &ok)));
+    if (ok) return HJ3D_OK;
+  }
   ProbePlan<KeyT> pl;
   HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
   if (!pl.n_work) return HJ3D_OK;
@@ -726,6 +809,11 @@ template <int HASH>
 int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
   if (!src.n) return HJ3D_OK;
+  if (!src.gather) {
+    bool ok = false;
+    HJ_TRY((probe_cluster_impl<HASH, 1>(c, t, src, flags, out, cap, &ok)));
+    if (ok) return HJ3D_OK;
+  }
   ProbePlan<KeyT> pl;
   HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
   if (!pl.n_work) return HJ3D_OK;
@@ -823,6 +911,7 @@ int hj3d_ctx_create(int device, hj3d_ctx** out) {
   hj3d_ctx* c = new hj3d_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
   CUDA_TRY(cudaDeviceGetDefaultMemPool(&c->pool, device));
@@ -877,6 +966,10 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PART_THREADS: if (v == 256 || v == 512 || v == 1024) c->part_threads = v; break;
     case HJ3D_OPT_PART_RANK_MATCH: c->part_rank_match = v != 0; break;
     case HJ3D_OPT_PROBE_THREADS: if (v == 256 || v == 512) c->probe_threads = v; break;
+    case HJ3D_OPT_CLUSTER_PROBE: c->cluster_probe = v != 0; break;
+    case HJ3D_OPT_CLUSTER_MIN_PROBE: c->cluster_min_probe = v; break;
+    case HJ3D_OPT_CLUSTER_MIN_PARTS: if (v >= 1) c->cluster_min_parts = v; break;
+    case HJ3D_OPT_CLUSTER_SLICE_BYTES: c->cluster_slice_bytes = v > 0 ? (v & ~15ll) : 0; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }
   return HJ3D_OK;
@@ -1257,6 +1350,18 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
 }
 
 }  // extern "C"
+
+#ifdef HJ3D_CL_TRACE
+extern "C" int hj3d_debug_trace_read(long long* h_rows, unsigned* n) {
+  unsigned cnt = 0;
+  cudaMemcpyFromSymbol(&cnt, hj3d::g_cl_trace_n, sizeof(cnt));
+  cudaMemcpyFromSymbol(h_rows, hj3d::g_cl_trace, sizeof(long long) * hj3d::kTraceRows * hj3d::kTraceCols);
+  unsigned zero = 0;
+  cudaMemcpyToSymbol(hj3d::g_cl_trace_n, &zero, sizeof(zero));
+  *n = cnt < (unsigned)hj3d::kTraceRows ? cnt : (unsigned)hj3d::kTraceRows;
+  return 0;
+}
+#endif
 
 template <int HASH>
 static int partition_by_owner_t(hj3d_ctx* c, Src src, Dir d, uint32_t width, uint32_t n_owners, uint32_t rowid_base,

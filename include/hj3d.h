@@ -65,6 +65,10 @@ extern "C" {
 #define HJ3D_OPT_SMEM_BUILD      12 /* 0/1: build chaining tables range-by-range in shared memory (default 1)    */
 #define HJ3D_OPT_SMEM_BUILD_BYTES 13 /* shared memory budget of one build range (default 64 KiB)               */
 #define HJ3D_OPT_PROBE_THREADS   11 /* shared-memory probe block size: 256 or 512 (default 256)                  */
+#define HJ3D_OPT_CLUSTER_PROBE   14 /* 0/1: probe coarse partitions with thread-block clusters over DSMEM (default 0: experimental) */
+#define HJ3D_OPT_CLUSTER_MIN_PROBE 15 /* probe inputs smaller than this use the other paths (default 2^22)         */
+#define HJ3D_OPT_CLUSTER_MIN_PARTS 16 /* coarse partitions needed before the cluster probe is used (default 64)    */
+#define HJ3D_OPT_CLUSTER_SLICE_BYTES 17 /* cap on the shared memory used for a CTA's table slice (default: all there is) */
 #define HJ3D_OPT_PART_RANK_MATCH 10 /* 0: rank by shared-memory atomics (default), 1: warp-private histograms + match_any (slower on B200) */
 
 /*

@@ -35,9 +35,9 @@ def pkg():
     return hj3d_loader.load()
 
 
-@pytest.fixture(scope="session", params=["direct", "partitioned", "smem"])
+@pytest.fixture(scope="session", params=["direct", "partitioned", "smem", "cluster"])
 def ctx(pkg, request):
-    """Every GPU test runs on all three probe paths: in place with global-memory lookups (small inputs),
+    """Every GPU test runs on all four probe paths: in place with global-memory lookups (small inputs),
     bucket-range partitioned with L2-window lookups, and partitioned into fine partitions probed in
     shared memory (what large inputs take), the latter two forced on at test sizes."""
     import torch
@@ -62,5 +62,12 @@ def ctx(pkg, request):
         c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
         c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096)
         c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
+    if request.param == "cluster":
+        # thread-block-cluster probe (what 2^30-row probe sides take), forced on at test sizes; tiny slices so
+        # that small directories still split into several coarse partitions and some slices overflow
+        c.set_option(pkg.capi.OPT_CLUSTER_PROBE, 1)
+        c.set_option(pkg.capi.OPT_CLUSTER_MIN_PROBE, 0)
+        c.set_option(pkg.capi.OPT_CLUSTER_MIN_PARTS, 1)
+        c.set_option(pkg.capi.OPT_CLUSTER_SLICE_BYTES, 8192)
     c.mode = request.param
     return c

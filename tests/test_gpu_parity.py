@@ -108,7 +108,7 @@ def test_partition_overflow_falls_back_to_exact_regions(pkg, ctx, oracle):
     B[:, 1] = np.where(rng.random(nB) < 0.9, hot, rng.integers(0, 1 << 20, nB)).astype(np.uint32)
     P = np.zeros((nP, 2), np.uint32)
     P[:, 0] = np.where(rng.random(nP) < 0.0001, hot, rng.integers(0, 1 << 20, nP)).astype(np.uint32)
-    old_window = 65536 if ctx.mode == "smem" else 2048
+    old_window = {"smem": 65536, "partitioned": 2048}.get(ctx.mode, 8 << 20)
     ctx.set_option(pkg.OPT_PARTITION_WINDOW, 1 << 20)          # few, large partitions
     try:
         for mode in (0, 3):
