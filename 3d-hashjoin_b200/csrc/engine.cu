@@ -15,6 +15,7 @@
 #include "probe.cuh"
 #include "probe_smem.cuh"
 #include "probe_cluster.cuh"
+#include "probe_fine.cuh"
 #include "scan.cuh"
 
 using namespace hj3d;
@@ -59,6 +60,7 @@ struct hj3d_ctx {
   int64_t cluster_min_probe = 1ll << 22;    // smaller probe inputs use the other paths
   int64_t cluster_min_parts = 64;           // coarse partitions needed to keep every cluster busy
   int64_t cluster_slice_bytes = 0;          // > 0: cap on the slice's shared memory (tests)
+  int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
   int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // per-phase events of the last call
   cudaEvent_t ev[PH_COUNT][2];
@@ -776,7 +778,16 @@ int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Slot<KeyT>* slots = (const Slot<KeyT>*)t->slots;
   const uint32_t nb = pl.n_work;
-  if (pl.smem) {
+  if (pl.smem && pl.recs && unique && c->lean_probe) {
+    const size_t sm = pl.fc.smem_bytes;
+    const Slot<KeyT>* recs = (const Slot<KeyT>*)pl.src.base;
+#define LAUNCH_PF(C, W) do { \
+      CUDA_TRY(cudaFuncSetAttribute(k_probe_fine<HASH, 0, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      k_probe_fine<HASH, 0, C, W><<<nb, kFineThreads, sm, c->stream>>>(recs, t->dir, pl.fc, pl.work, pl.work_part, t->off, (const void*)slots, out, cap, c->d_ctr); } while (0)
+    if (cs) { if (wr) LAUNCH_PF(true, true); else LAUNCH_PF(true, false); }
+    else    { if (wr) LAUNCH_PF(false, true); else LAUNCH_PF(false, false); }
+#undef LAUNCH_PF
+  } else if (pl.smem) {
     const size_t sm = pl.fc.smem_bytes;
 #define LAUNCH_PS3(U, C, W, R, T) do { \
       CUDA_TRY(cudaFuncSetAttribute(k_probe_chaining_smem<HASH, U, C, W, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
@@ -821,7 +832,16 @@ int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
   const uint32_t nb = pl.n_work;
-  if (pl.smem) {
+  if (pl.smem && pl.recs && c->lean_probe) {
+    const size_t sm = pl.fc.smem_bytes;
+    const Slot<KeyT>* recs = (const Slot<KeyT>*)pl.src.base;
+#define LAUNCH_PF(C, W) do { \
+      CUDA_TRY(cudaFuncSetAttribute(k_probe_fine<HASH, 1, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      k_probe_fine<HASH, 1, C, W><<<nb, kFineThreads, sm, c->stream>>>(recs, t->dir, pl.fc, pl.work, pl.work_part, t->goff, (const void*)groups, out, cap, c->d_ctr); } while (0)
+    if (cs) { if (wr) LAUNCH_PF(true, true); else LAUNCH_PF(true, false); }
+    else    { if (wr) LAUNCH_PF(false, true); else LAUNCH_PF(false, false); }
+#undef LAUNCH_PF
+  } else if (pl.smem) {
     const size_t sm = pl.fc.smem_bytes;
 #define LAUNCH_NS3(C, W, R, T) do { \
       CUDA_TRY(cudaFuncSetAttribute(k_probe_nested_smem<HASH, C, W, R, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
@@ -969,6 +989,7 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_CLUSTER_PROBE: c->cluster_probe = v != 0; break;
     case HJ3D_OPT_CLUSTER_MIN_PROBE: c->cluster_min_probe = v; break;
     case HJ3D_OPT_CLUSTER_MIN_PARTS: if (v >= 1) c->cluster_min_parts = v; break;
+    case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
     case HJ3D_OPT_CLUSTER_SLICE_BYTES: c->cluster_slice_bytes = v > 0 ? (v & ~15ll) : 0; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }
