@@ -16,6 +16,7 @@
 #include "probe_smem.cuh"
 #include "probe_cluster.cuh"
 #include "probe_fine.cuh"
+#include "unnest.cuh"
 #include "scan.cuh"
 
 using namespace hj3d;
@@ -870,29 +871,48 @@ template <class KeyT>
 int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t* gref, uint64_t n, uint32_t flags,
                 uint2* out, uint64_t cap, hj3d_counters* res) {
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
-  unsigned long long* offsets = nullptr;
-  HJ_TRY(dev_alloc(c, &offsets, n + 1));
-  HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
-                                                (DevStats*)nullptr, c->d_scalar)));
-  unsigned long long* h_tot = (unsigned long long*)c->h_pinned;
-  CUDA_TRY(cudaMemcpyAsync(h_tot, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  const unsigned long long total = *h_tot;
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
-  if (total && (cs || wr)) {
-    const uint32_t nb = (uint32_t)((total + kUnnestTile - 1) / kUnnestTile);
-#define LAUNCH_UN(C, W) k_unnest<KeyT, C, W><<<nb, kUnnestThreads, 0, c->stream>>>(left, gref, n, offsets, groups, t->rows, out, cap, c->d_ctr)
+  unsigned long long total = 0;
+  unsigned long long* h = (unsigned long long*)c->h_pinned;
+  // warp-cooperative expansion (unnest.cuh): per-block sums -> scan -> expand
+  const uint32_t nb = blocks_for(n, kUxTile);
+  unsigned long long *sums = nullptr, *bases = nullptr;
+  HJ_TRY(dev_alloc(c, &sums, (uint64_t)nb + 1));
+  HJ_TRY(dev_alloc(c, &bases, (uint64_t)nb + 1));
+  CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 16, c->stream));
+  if (nb) {
+    k_unnest_count<KeyT><<<nb, kUxThreads, 0, c->stream>>>(gref, n, groups, sums, c->d_scalar + 1);
+    ++c->launches;
+  }
+  if (nb) HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{sums}, StoreExU64{bases}, nb, (DevStats*)nullptr, c->d_scalar)));
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_scalar, 16, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  total = nb ? h[0] : 0;
+  const bool hot = h[1] > kUnnestWarpMax;                  // a group too long for one warp: element-balanced kernel
+  if (total && (cs || wr) && !hot) {
+#define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(left, gref, n, groups, t->rows, bases, out, cap, c->d_ctr)
+    if (cs) { if (wr) LAUNCH_UX(true, true); else LAUNCH_UX(true, false); }
+    else    { LAUNCH_UX(false, true); }
+#undef LAUNCH_UX
+    ++c->launches;
+  } else if (total && (cs || wr)) {
+    unsigned long long* offsets = nullptr;
+    HJ_TRY(dev_alloc(c, &offsets, n + 1));
+    HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
+                                                  (DevStats*)nullptr, c->d_scalar)));
+    const uint32_t nbe = (uint32_t)((total + kUnnestTile - 1) / kUnnestTile);
+#define LAUNCH_UN(C, W) k_unnest<KeyT, C, W><<<nbe, kUnnestThreads, 0, c->stream>>>(left, gref, n, offsets, groups, t->rows, out, cap, c->d_ctr)
     if (cs) { if (wr) LAUNCH_UN(true, true); else LAUNCH_UN(true, false); }
     else    { LAUNCH_UN(false, true); }
 #undef LAUNCH_UN
     ++c->launches;
   }
-  DevCounters* h = (DevCounters*)c->h_pinned;
-  CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  DevCounters* hc = (DevCounters*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(hc, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   res->matches = total; res->out_tuples = total; res->num_cmps = 0;     // AlgUnnestHt::_count = #outputs (algebra.hh:486-487)
-  res->checksum_sum = h->checksum_sum; res->checksum_xor = h->checksum_xor;
+  res->checksum_sum = hc->checksum_sum; res->checksum_xor = hc->checksum_xor;
   res->overflow = (wr && total > cap) ? 1 : 0;
   res->out_written = wr ? (total > cap ? cap : total) : 0;
   return HJ3D_OK;
