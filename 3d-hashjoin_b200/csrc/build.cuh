@@ -266,11 +266,11 @@ k_order_groups(const uint32_t* __restrict__ goff, Group<KeyT>* __restrict__ grou
 // statistics of makeStatistics are reduced on the way.  base[f] = number of build records in
 // partitions < f.  A partition with more than `cap_recs` records sets *overflow and is skipped (the
 // caller then rebuilds with the global-memory kernels).
-constexpr int kFineBuildThreads = 512;
+constexpr int kFineBuildThreads = 256;   // ~95 registers: 512-thread blocks fit one per SM, 256-thread blocks two or more
 constexpr int kFineBuildItems   = 12;
 
 template <int HASH>
-__global__ void __launch_bounds__(kFineBuildThreads)
+__global__ void __launch_bounds__(kFineBuildThreads, 2)
 k_build_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
              const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
              const unsigned long long* __restrict__ base, Dir d, uint32_t width, uint32_t n_fine, uint32_t cap_recs,
@@ -318,7 +318,7 @@ k_build_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
   {
     DevAgg all{~0ull, 0, 0, 0, 0}, ne{~0ull, 0, 0, 0, 0};
     unsigned long long empty = 0;
-    constexpr uint32_t PER = 8;                              // width <= 4096 = 512 threads x 8
+    constexpr uint32_t PER = 8;                              // width <= 2048 = 256 threads x 8
     const uint32_t a = threadIdx.x * PER;
     uint32_t v[PER], sum = 0;
 #pragma unroll
@@ -336,10 +336,11 @@ k_build_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
 #pragma unroll
     for (uint32_t k = 0; k < PER; ++k) { if (a + k < nbk) sm_off[a + k] = ex; ex += v[k]; }
     if (threadIdx.x == 0) sm_off[nbk] = cnt;
-    agg_commit(all, &stats->all, sm_red);
-    agg_commit(ne, &stats->nonempty, sm_red);
+    DevStats* my_stats = stats + (blockIdx.x & 63u);                   // replica (engine.cu: kStatsCopies = 64)
+    agg_commit(all, &my_stats->all, sm_red);
+    agg_commit(ne, &my_stats->nonempty, sm_red);
     empty = warp_sum(empty);
-    if (lane_id() == 0 && empty) atomicAdd(&stats->empty, empty);
+    if (lane_id() == 0 && empty) atomicAdd(&my_stats->empty, empty);
   }
   __syncthreads();
   // ---- place the records

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "build.cuh"
+#include "build_nested_fine.cuh"
 #include "common.cuh"
 #include "partition.cuh"
 #include "probe.cuh"
@@ -239,8 +240,34 @@ template <class KeyT> struct LoadGroupLen {
 struct LoadU64 { const unsigned long long* p; __device__ unsigned long long operator()(uint64_t i) const { return p[i]; } };
 struct StoreExU64 { unsigned long long* p; __device__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const { p[i] = ex; } };
 
+// The fine build kernels commit their bucket statistics once per block; with 10^5..10^6 blocks the atomics on ONE
+// DevStats serialise in the L2 (measured: most of a 47 ms nested build).  Blocks therefore spread over kStatsCopies
+// replicas (block id & mask) that one tiny kernel folds into replica 0 afterwards.
+constexpr int kStatsCopies = 64;
+__global__ void k_stats_fold(DevStats* s, int copies) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  DevStats r = s[0];
+  for (int i = 1; i < copies; ++i) {
+    const DevStats& o = s[i];
+    r.all.mn = o.all.mn < r.all.mn ? o.all.mn : r.all.mn; r.all.mx = o.all.mx > r.all.mx ? o.all.mx : r.all.mx;
+    r.all.sum += o.all.sum; r.all.sumsq += o.all.sumsq; r.all.cnt += o.all.cnt;
+    r.nonempty.mn = o.nonempty.mn < r.nonempty.mn ? o.nonempty.mn : r.nonempty.mn;
+    r.nonempty.mx = o.nonempty.mx > r.nonempty.mx ? o.nonempty.mx : r.nonempty.mx;
+    r.nonempty.sum += o.nonempty.sum; r.nonempty.sumsq += o.nonempty.sumsq; r.nonempty.cnt += o.nonempty.cnt;
+    r.empty += o.empty;
+  }
+  s[0] = r;
+}
+
 void init_dev_stats_host(DevStats& s) {
   s.all = DevAgg{~0ull, 0, 0, 0, 0}; s.nonempty = DevAgg{~0ull, 0, 0, 0, 0}; s.empty = 0;
+}
+
+int init_dev_stats_copies(hj3d_ctx* c) {
+  static DevStats h[kStatsCopies];
+  for (int i = 0; i < kStatsCopies; ++i) init_dev_stats_host(h[i]);
+  CUDA_TRY(cudaMemcpyAsync(c->d_stats, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  return HJ3D_OK;
 }
 
 // clear(): the table becomes empty but keeps its device buffers for the next build of the repeat loop
@@ -433,8 +460,10 @@ int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT
     const double per_bucket = 4.0 + (double)n * sizeof(Slot<KeyT>) / (double)(nl ? nl : 1);
     double w = 0.85 * (double)c->smem_build_bytes / per_bucket;
     Wf = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
-    if (Wf > 4096) Wf = 4096;
+    if (Wf > 2048) Wf = 2048;
     if (Wf < nl) { uint32_t p2 = 1; while (p2 * 2 <= Wf) p2 *= 2; Wf = p2; }
+    // the block keeps its records in registers: expected records per range + 25% must fit
+    while (Wf > 1 && (double)n / (double)(nl ? nl : 1) * Wf * 1.25 + 256.0 > (double)(kFineBuildThreads * kFineBuildItems)) Wf >>= 1;
   }
   const uint32_t F = nl ? (nl + Wf - 1) / Wf : 1;
   if (!c->smem_build || (int64_t)n < c->smem_min_probe || F < 2) return HJ3D_OK;
@@ -461,13 +490,85 @@ int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT
   // ranges past fine.P (two-level rounding never creates them; one-level has exactly F) -> grid = F
   k_build_fine<HASH><<<F, kFineBuildThreads, sm, c->stream>>>(fine.recs, fine.part_start, fine.counts, base, t->dir, Wf, fine.P,
                                                               cap_recs, t->off, slots, c->d_stats, d_flag);
-  ++c->launches;
+  k_stats_fold<<<1, 32, 0, c->stream>>>(c->d_stats, kStatsCopies);
+  c->launches += 2;
   uint32_t* h = (uint32_t*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(h, d_flag, 4, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   if (*h) return HJ3D_OK;                                   // some range overflowed shared memory
   (void)nl;
+  *done = true;
+  return HJ3D_OK;
+}
+
+// Nested tables over large inputs: the same fine bucket ranges, grouped by key in shared memory
+// (build_nested_fine.cuh).  *done = false: a range or a bucket is too large (skew) -> global-memory kernels.
+template <int HASH>
+int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done) {
+  using KeyT = typename HashT<HASH>::key_t;
+  *done = false;
+  const uint64_t n = src.n;
+  const uint32_t nl = t->dir.n_local;
+  uint32_t Wf;
+  {
+    const double per_bucket = 8.0 + (double)n * sizeof(Slot<KeyT>) / (double)(nl ? nl : 1);
+    double w = 0.85 * (double)c->smem_build_bytes / per_bucket;
+    Wf = w >= (double)nl ? nl : (w < 1.0 ? 1u : (uint32_t)w);
+    if (Wf > 2048) Wf = 2048;
+    if (Wf < nl) { uint32_t p2 = 1; while (p2 * 2 <= Wf) p2 *= 2; Wf = p2; }
+    // the block keeps its records in registers: expected records per range + 25% must fit
+    while (Wf > 1 && (double)n / (double)(nl ? nl : 1) * Wf * 1.25 + 256.0 > (double)(kNfThreads * kNfItems)) Wf >>= 1;
+  }
+  const uint32_t F = nl ? (nl + Wf - 1) / Wf : 1;
+  if (!c->smem_build || (int64_t)n < c->smem_min_probe || F < 2) return HJ3D_OK;
+  if ((double)n * 1.08 + 4096.0 * (double)F >= 4.0e9) return HJ3D_OK;
+  Partitioned<KeyT> fine;
+  bool ok = false;
+  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok)));
+  if (!ok) return HJ3D_OK;
+  PhaseTimer pt(c, PH_GROUP);
+  unsigned long long* base = nullptr;
+  HJ_TRY(dev_alloc(c, &base, (uint64_t)fine.P + 1));
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{base}, fine.P, (DevStats*)nullptr, (unsigned long long*)nullptr)));
+  const uint32_t hdr_bytes = (2 * (Wf + 1) * 4 + 15) & ~15u;
+  uint32_t cap_recs = kNfThreads * kNfItems;
+  const uint32_t smem_max = 160u << 10;
+  if (hdr_bytes + (uint64_t)cap_recs * (sizeof(Slot<KeyT>) + 1) > smem_max) cap_recs = (smem_max - hdr_bytes) / (sizeof(Slot<KeyT>) + 1);
+  const uint64_t expect = n / F + n / (2ull * F) + 512;                      // expected records per range + 50% + 512
+  if (expect < cap_recs) cap_recs = (uint32_t)expect;
+  cap_recs &= ~15u;
+  const size_t sm = hdr_bytes + (size_t)cap_recs * (sizeof(Slot<KeyT>) + 1);  // records + one leader flag byte each
+  Group<KeyT>* gtmp = nullptr;                                             // one slot per build row: #groups is only known afterwards
+  unsigned long long* lookback = nullptr;
+  HJ_TRY(dev_alloc(c, &gtmp, n));
+  HJ_TRY(dev_alloc(c, &lookback, (uint64_t)F));
+  HJ_TRY(buf_ensure(c, t->b_goff, &t->goff, (uint64_t)nl + 1));
+  HJ_TRY(buf_ensure(c, t->b_rows, &t->rows, n));
+  CUDA_TRY(cudaMemsetAsync(lookback, 0, (size_t)F * 8, c->stream));
+  uint32_t* d_flag = (uint32_t*)(c->d_scalar + 2);
+  CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 4 * sizeof(unsigned long long), c->stream));
+  HJ_TRY(init_dev_stats_copies(c));
+  CUDA_TRY(cudaFuncSetAttribute(k_build_fine_nested<HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  k_build_fine_nested<HASH><<<F, kNfThreads, sm, c->stream>>>(fine.recs, fine.part_start, fine.counts, base, t->dir, Wf, F, cap_recs,
+                                                              t->goff, gtmp, t->rows, lookback, c->d_stats, d_flag, c->d_scalar);
+  k_stats_fold<<<1, 32, 0, c->stream>>>(c->d_stats, kStatsCopies);
+  c->launches += 2;
+  unsigned long long* h = (unsigned long long*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_scalar, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  if (*(uint32_t*)(h + 2)) return HJ3D_OK;                                  // a range / bucket overflowed shared memory
+  const uint64_t G = h[0];
+  Group<KeyT>* groups = nullptr;
+  HJ_TRY(buf_ensure(c, t->b_groups, &groups, G));
+  if (G) CUDA_TRY(cudaMemcpyAsync(groups, gtmp, G * sizeof(Group<KeyT>), cudaMemcpyDeviceToDevice, c->stream));
+  t->groups = groups; t->n_groups = G; t->n = n; t->slots = nullptr;
+  t->parts = 1; t->part_width = nl ? nl : 1;
+  CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  set_fine_width(c, t, (double)G * sizeof(Group<KeyT>));
+  t->have_stats = true; t->built = true;
   *done = true;
   return HJ3D_OK;
 }
@@ -479,15 +580,19 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   const uint32_t nl = t->dir.n_local;
   const Dir d = t->dir;
   const bool agg = c->warp_aggregate != 0;
-  HJ_TRY(buf_ensure(c, t->b_off, &t->off, (uint64_t)nl + 1));
   Slot<KeyT>* slots = nullptr;
+  if (t->kind == HJ3D_NESTED) {
+    bool done = false;
+    HJ_TRY(build_nested_fine<HASH>(c, t, src, &done));
+    if (done) return HJ3D_OK;
+  }
+  HJ_TRY(buf_ensure(c, t->b_off, &t->off, (uint64_t)nl + 1));
   if (t->kind == HJ3D_CHAINING) HJ_TRY(buf_ensure(c, t->b_slots, &slots, n));
   else                          HJ_TRY(dev_alloc(c, &slots, n));          // nested: only needed during the build
   t->slots = slots;
   if (t->kind == HJ3D_CHAINING) {
     set_fine_width(c, t, (double)n * sizeof(Slot<KeyT>));
-    DevStats hs0; init_dev_stats_host(hs0);
-    CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs0, sizeof(hs0), cudaMemcpyHostToDevice, c->stream));
+    HJ_TRY(init_dev_stats_copies(c));
     bool done = false;
     HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done));
     if (done) {
@@ -960,7 +1065,7 @@ int hj3d_ctx_create(int device, hj3d_ctx** out) {
   for (int i = 0; i < PH_COUNT; ++i) { CUDA_TRY(cudaEventCreate(&c->ev[i][0])); CUDA_TRY(cudaEventCreate(&c->ev[i][1])); c->ev_used[i] = false; }
   CUDA_TRY(cudaEventCreate(&c->ev_total[0])); CUDA_TRY(cudaEventCreate(&c->ev_total[1]));
   CUDA_TRY(cudaMalloc((void**)&c->d_ctr, sizeof(DevCounters)));
-  CUDA_TRY(cudaMalloc((void**)&c->d_stats, sizeof(DevStats)));
+  CUDA_TRY(cudaMalloc((void**)&c->d_stats, kStatsCopies * sizeof(DevStats)));
   CUDA_TRY(cudaMalloc((void**)&c->d_scalar, 4 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMallocHost(&c->h_pinned, 16384));
   *out = c;
