@@ -332,6 +332,38 @@ def run_ours(args):
     # size-independent correctness properties at full size: every S tuple finds exactly one R partner
     assert out_total == nS, f"join produced {out_total} tuples, expected |S| = {nS}"
     value = (nR + nS) / (ms * 1e-3)
+    # ---- the other table variant on the same relations (N=1, default plan only): nested 3D table + deferred unnest
+    other = None
+    if world == 1 and args.plan == "Csr" and not args.no_other_plans:
+        try:
+            t2 = ctx.table(pkg.NESTED, D)
+            nest2 = torch.empty((nS, 2), dtype=torch.int32, device=dev)
+            def step_nsr():
+                t2.clear()
+                t2.build(B, nBl, ksB)
+                b_ms = ctx.timings()["total_ms"]
+                rc_, c_ = t2.probe_nested(P, nPl, ksP, flags=0, out=nest2, out_cap=nS)
+                p_ms = ctx.timings()["total_ms"]
+                m_ = c_["out_written"]
+                l_, g_ = nest2[:m_, 0].contiguous(), nest2[:m_, 1].contiguous()
+                rc_, r_ = t2.unnest(l_, g_, m_, flags=0, out=out, out_cap=cap_out)
+                return r_, b_ms, p_ms, ctx.timings()["unnest_ms"]
+            for _ in range(2):
+                step_nsr()
+            torch.cuda.synchronize(); a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                r_, b_ms, p_ms, u_ms = step_nsr()
+            a1.record(); torch.cuda.synchronize()
+            ms2 = a0.elapsed_time(a1) / 3
+            assert r_["out_tuples"] == nS
+            other = {"Nsr": {"ms_per_step": ms2, "value": (nR + nS) / (ms2 * 1e-3), "unit": "tuples/s", "steps": 3, "warmup": 2,
+                             "build_ms": b_ms, "probe_call_ms": p_ms, "unnest_ms": u_ms,
+                             "join_frac": algorithmic_bytes(nBg, nPg, nS, nS, D, nested=True) / (ms2 * 1e-3) / 1e9 / peaks()[0],
+                             "note": "nested 3D table + nested probe + deferred unnest (plan Nsr) on the same relations"}}
+            t2.destroy(); del nest2
+        except Exception as ex:
+            other = {"Nsr": {"error": repr(ex)}}
     # ---- e2e: host buffers through hj3d_join_host (H2D of both relations + D2H of the counters inside)
     e2e = None
     if world == 1 and not args.no_e2e:
@@ -363,29 +395,39 @@ def run_ours(args):
         return
     peak, peak_src = peaks()
     nested = mode == 3
+    nested_plan = nested
     nM = state["probe_counters"]["matches"] if nested else 0
     alg = algorithmic_bytes(nBg, nPg, nM * world if nested else 0, nS, D, nested=nested)
-    # dominant kernel: the probe kernel.  32 B per probe tuple: 12 B tuple + 4 B directory word + 8 B slot + 8 B result pair
+    # dominant kernel of the step (largest share in profiles/*launches*): the shared-memory probe kernel.  Bytes that ONE
+    # launch must move: per probe tuple the 8-byte (key, id) record it reads and the 8-byte result pair it writes, plus
+    # the table slices it stages once (4-byte directory word per bucket + 8-byte slot / 16-byte group per build row).
+    # (The 12-byte row-store tuples are read by the partition pass, not by this kernel; join_frac below charges the
+    # whole join, partition passes included, against SURVEY 8(d)'s algorithmic bytes.)
     pm = sum(probe_ms) / len(probe_ms)
-    probe_bytes = state["n_probe_local"] * (12 + 4 + 8 + 8)
+    n_res = res["out_tuples"] if not nested_plan else state["probe_counters"]["matches"]
+    table_bytes = 4 * (D // world) + (nBg // world) * 8 if not nested_plan else 4 * (D // world) + 16 * min(nBg, D) // world
+    probe_bytes = state["n_probe_local"] * 8 + n_res * 8 + table_bytes
     line = {"metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e if e2e is not None else {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                                "note": "e2e is measured at N=1"},
-            "roofline": {"bound": "hbm", "kernel": "k_probe_chaining" if mode <= 1 else "k_probe_nested",
+            "roofline": {"bound": "hbm", "kernel": {1: "k_probe_fine<chaining, IsBuildKeyUnique>", 0: "k_probe_chaining_smem", 3: "k_probe_fine<nested>"}[mode],
                          "achieved": probe_bytes / (pm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": probe_bytes / (pm * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": pm, "algorithmic_bytes_per_launch": probe_bytes,
                          "join_algorithmic_bytes": alg, "join_frac": alg / (ms * 1e-3) / 1e9 / peak / world},
             "phases_ms": {"build_total": sum(build_ms) / len(build_ms), "histogram": state["build"]["histogram_ms"],
                           "scan": state["build"]["scan_ms"], "scatter": state["build"]["scatter_ms"],
-                          "group": state["build"]["group_ms"], "probe": pm, "unnest": state.get("unnest_ms", 0.0)},
+                          "group": state["build"]["group_ms"], "build_partition": state["build"]["partition_ms"],
+                          "probe_partition": state["probe"]["partition_ms"], "probe": pm, "unnest": state.get("unnest_ms", 0.0)},
             "result": {"out_tuples": out_total, "num_cmps": cmps_total, "verified_checksum": verified,
                        "checksum_in_timed_steps": bool(args.checksum)}}
     if world > 1:
         line["shuffle"] = {"bytes_sent_per_gpu": state["shuffle_bytes"], "note": "NCCL all_to_all_single of (key,row id) records"}
+    if other is not None:
+        line["other_plans"] = other
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(args)
     print(json.dumps(line), flush=True)
@@ -406,6 +448,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the nested plan (N=1)")
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (HJ3D_OPT_*), repeatable")
