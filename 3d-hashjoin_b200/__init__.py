@@ -156,5 +156,12 @@ class Table:
                                              int(out_cap), C.byref(c)))
         return rc, c.as_dict()
 
+    def unnest_pairs(self, nested_pairs, n, flags=F_CHECKSUM, out=None, out_cap=0):
+        """deferred unnest of the (left, group ref) pairs exactly as probe_nested wrote them"""
+        c = Counters()
+        rc = capi.check(self.lib.hj3d_unnest_pairs(self.ctx.h, self.h, _ptr(nested_pairs), int(n), flags, _ptr(out),
+                                                   int(out_cap), C.byref(c)))
+        return rc, c.as_dict()
+
     def group_first_row(self, gref, n, out):
         capi.check(self.lib.hj3d_group_first_row(self.ctx.h, self.h, _ptr(gref), int(n), _ptr(out)))

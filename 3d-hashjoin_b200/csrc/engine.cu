@@ -973,8 +973,9 @@ int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2
 }
 
 template <class KeyT>
-int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t* gref, uint64_t n, uint32_t flags,
+int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t* gref, const uint2* pairs, uint64_t n, uint32_t flags,
                 uint2* out, uint64_t cap, hj3d_counters* res) {
+  const NestedIn in{left, gref, pairs};
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
   unsigned long long total = 0;
@@ -986,7 +987,7 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   HJ_TRY(dev_alloc(c, &bases, (uint64_t)nb + 1));
   CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 16, c->stream));
   if (nb) {
-    k_unnest_count<KeyT><<<nb, kUxThreads, 0, c->stream>>>(gref, n, groups, sums, c->d_scalar + 1);
+    k_unnest_count<KeyT><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, sums, c->d_scalar + 1);
     ++c->launches;
   }
   if (nb) HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{sums}, StoreExU64{bases}, nb, (DevStats*)nullptr, c->d_scalar)));
@@ -995,12 +996,19 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   total = nb ? h[0] : 0;
   const bool hot = h[1] > kUnnestWarpMax;                  // a group too long for one warp: element-balanced kernel
   if (total && (cs || wr) && !hot) {
-#define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(left, gref, n, groups, t->rows, bases, out, cap, c->d_ctr)
+#define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, t->rows, bases, out, cap, c->d_ctr)
     if (cs) { if (wr) LAUNCH_UX(true, true); else LAUNCH_UX(true, false); }
     else    { LAUNCH_UX(false, true); }
 #undef LAUNCH_UX
     ++c->launches;
   } else if (total && (cs || wr)) {
+    if (pairs) {                                           // the element-balanced kernel reads two columns
+      uint32_t *l2 = nullptr, *g2 = nullptr;
+      HJ_TRY(dev_alloc(c, &l2, n)); HJ_TRY(dev_alloc(c, &g2, n));
+      k_split_pairs<<<blocks_for(n, 256), 256, 0, c->stream>>>(pairs, n, l2, g2);
+      ++c->launches;
+      left = l2; gref = g2;
+    }
     unsigned long long* offsets = nullptr;
     HJ_TRY(dev_alloc(c, &offsets, n + 1));
     HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
@@ -1390,8 +1398,30 @@ int hj3d_unnest(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_left, const uint32
   int rc;
   {
     PhaseTimer pt(c, PH_UNNEST);
-    if (t->key_bytes == 8) rc = unnest_impl<uint64_t>(c, t, d_left, d_gref, n, flags, (uint2*)d_out, cap, out);
-    else                   rc = unnest_impl<uint32_t>(c, t, d_left, d_gref, n, flags, (uint2*)d_out, cap, out);
+    if (t->key_bytes == 8) rc = unnest_impl<uint64_t>(c, t, d_left, d_gref, nullptr, n, flags, (uint2*)d_out, cap, out);
+    else                   rc = unnest_impl<uint32_t>(c, t, d_left, d_gref, nullptr, n, flags, (uint2*)d_out, cap, out);
+  }
+  end_call(c);
+  if (rc < 0) return rc;
+  return out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_unnest_pairs(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_nested_pairs, uint64_t n,
+                      uint32_t flags, uint32_t* d_out, uint64_t cap, hj3d_counters* out) {
+  if (!c || !t || !out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_NESTED) return fail(HJ3D_ERR_INVALID, "hj3d_unnest_pairs needs a nested table");
+  if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
+  if (n && !d_nested_pairs) return fail(HJ3D_ERR_INVALID, "NULL input");
+  CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  memset(out, 0, sizeof(*out));
+  int rc;
+  {
+    PhaseTimer pt(c, PH_UNNEST);
+    if (t->key_bytes == 8) rc = unnest_impl<uint64_t>(c, t, nullptr, nullptr, (const uint2*)d_nested_pairs, n, flags, (uint2*)d_out, cap, out);
+    else                   rc = unnest_impl<uint32_t>(c, t, nullptr, nullptr, (const uint2*)d_nested_pairs, n, flags, (uint2*)d_out, cap, out);
   }
   end_call(c);
   if (rc < 0) return rc;
@@ -1475,11 +1505,7 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
     rc = hj3d_probe_nested(c, t, hj.p, nP, ksP, nullptr, flags, (uint32_t*)hj.nest, nP, pc);
     if (rc < 0) return bail(rc);
     const uint64_t m = pc->out_written;
-    rc = ensure(&hj.l, &hj.cl, m * 4); if (rc < 0) return bail(rc);
-    rc = ensure(&hj.g, &hj.cg, m * 4); if (rc < 0) return bail(rc);
-    rc = hj3d_split_pairs(c, (const uint32_t*)hj.nest, m, (uint32_t*)hj.l, (uint32_t*)hj.g);
-    if (rc < 0) return bail(rc);
-    rc = hj3d_unnest(c, t, (const uint32_t*)hj.l, (const uint32_t*)hj.g, m, flags, dOut, cap, uc);
+    rc = hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, m, flags, dOut, cap, uc);
     if (rc < 0) return bail(rc);
     n_out = uc->out_written;
   }

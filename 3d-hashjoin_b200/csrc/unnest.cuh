@@ -32,9 +32,16 @@ template <> __device__ __forceinline__ uint2 group_start_len<uint32_t>(const Gro
   return __ldg(reinterpret_cast<const uint2*>(groups + g) + 1);           // {key, first_row | start, len}: one 8-byte load
 }
 
+// nested tuples come either as two columns (left[], gref[]) or as the (left, gref) pairs the nested probe wrote
+struct NestedIn {
+  const uint32_t* left; const uint32_t* gref; const uint2* pairs;
+  __device__ __forceinline__ uint32_t g(uint64_t i) const { return pairs ? __ldg(&pairs[i].y) : __ldg(gref + i); }
+  __device__ __forceinline__ uint2 lg(uint64_t i) const { return pairs ? __ldg(pairs + i) : make_uint2(__ldg(left + i), __ldg(gref + i)); }
+};
+
 template <class KeyT>
 __global__ void __launch_bounds__(kUxThreads)
-k_unnest_count(const uint32_t* __restrict__ gref, uint64_t n, const Group<KeyT>* __restrict__ groups,
+k_unnest_count(NestedIn in, uint64_t n, const Group<KeyT>* __restrict__ groups,
                unsigned long long* __restrict__ block_sums, unsigned long long* __restrict__ max_len) {
   __shared__ unsigned long long sm[kUxThreads / 32];
   const uint64_t base = (uint64_t)blockIdx.x * kUxTile + (threadIdx.x >> 5) * (32 * kUxRounds) + lane_id();
@@ -42,7 +49,7 @@ k_unnest_count(const uint32_t* __restrict__ gref, uint64_t n, const Group<KeyT>*
 #pragma unroll
   for (int j = 0; j < kUxRounds; ++j) {
     const uint64_t i = base + j * 32;
-    if (i < n) { const uint32_t len = group_start_len<KeyT>(groups, __ldg(gref + i)).y; sum += len; mx = len > mx ? len : mx; }
+    if (i < n) { const uint32_t len = group_start_len<KeyT>(groups, in.g(i)).y; sum += len; mx = len > mx ? len : mx; }
   }
   sum = warp_sum(sum); mx = warp_max(mx);
   if (lane_id() == 0) { sm[threadIdx.x >> 5] = sum; if (mx > kUnnestWarpMax) atomicMax(max_len, (unsigned long long)mx); }
@@ -57,7 +64,7 @@ k_unnest_count(const uint32_t* __restrict__ gref, uint64_t n, const Group<KeyT>*
 
 template <class KeyT, bool CHECKSUM, bool WRITE>
 __global__ void __launch_bounds__(kUxThreads)
-k_unnest_expand(const uint32_t* __restrict__ left, const uint32_t* __restrict__ gref, uint64_t n,
+k_unnest_expand(NestedIn in, uint64_t n,
                 const Group<KeyT>* __restrict__ groups, const uint32_t* __restrict__ rows,
                 const unsigned long long* __restrict__ block_base, uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
   __shared__ unsigned long long sm[kUxThreads / 32];
@@ -70,7 +77,7 @@ k_unnest_expand(const uint32_t* __restrict__ left, const uint32_t* __restrict__ 
   for (int j = 0; j < kUxRounds; ++j) {
     const uint64_t i = base + j * 32;
     uint32_t len = 0; lf[j] = 0; st[j] = 0;
-    if (i < n) { const uint2 g = group_start_len<KeyT>(groups, __ldg(gref + i)); st[j] = g.x; len = g.y; lf[j] = __ldg(left + i); }
+    if (i < n) { const uint2 t = in.lg(i); const uint2 g = group_start_len<KeyT>(groups, t.y); st[j] = g.x; len = g.y; lf[j] = t.x; }
     uint32_t inc = len;                                   // inclusive scan of the lengths of this round
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }

@@ -190,6 +190,9 @@ int hj3d_probe_nested(hj3d_ctx* ctx, hj3d_table* t, const void* d_probe, uint64_
                       uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
 int hj3d_unnest(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_left, const uint32_t* d_group_ref, uint64_t n,
                 uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
+/* same, reading the (left, group_ref) PAIRS exactly as hj3d_probe_nested wrote them (no column split in between) */
+int hj3d_unnest_pairs(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_nested_pairs, uint64_t n,
+                      uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
 /* first build row id (the MainNode's own tuple) of each group_ref: d_out[i] = data(group d_group_ref[i]) */
 int hj3d_group_first_row(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_group_ref, uint64_t n, uint32_t* d_out);
 /* d_dst[i] = d_src[2*d_idx_pairs_col...]: small column helpers for composing deferred-unnest pipelines */

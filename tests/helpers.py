@@ -112,6 +112,12 @@ def gpu_plan(pkg, ctx, mode, B, ksB, D, P, ksP, gather=None, materialize=True, f
             out = torch.zeros((max(n_out, 1), 2), dtype=torch.int32, device="cuda")
             rc, cu = t.unnest(left, gref, m, flags=flags, out=out, out_cap=n_out)
             res["unnest"] = cu
+            # the same unnest fed with the (left, group ref) pairs as the probe wrote them (no column split)
+            out2 = torch.zeros((max(n_out, 1), 2), dtype=torch.int32, device="cuda")
+            rc2, cu2 = t.unnest_pairs(nest, m, flags=flags, out=out2, out_cap=n_out)
+            assert rc2 == rc and cu2 == cu, (cu2, cu)
+            assert np.array_equal(sorted_pairs(out2[:cu2["out_written"]].cpu().numpy().view(np.uint32)),
+                                  sorted_pairs(out[:cu["out_written"]].cpu().numpy().view(np.uint32)))
             res["pairs"] = out[:cu["out_written"]].cpu().numpy().view(np.uint32)
     res["size"] = t.size()
     t.destroy()

@@ -62,8 +62,7 @@ def main():
                 rc, c = table.probe_nested(P, nP, ksP, flags=flags, out=nest, out_cap=nP)
                 tp = ctx.timings()
                 m = c["out_written"]
-                left, gref = nest[:m, 0].contiguous(), nest[:m, 1].contiguous()
-                rc, res = table.unnest(left, gref, m, flags=flags, out=out, out_cap=nS if out is not None else 0)
+                rc, res = table.unnest_pairs(nest, m, flags=flags, out=out, out_cap=nS if out is not None else 0)
                 tu = ctx.timings()
             e1.record(); torch.cuda.synchronize()
             rows.append({"total": e0.elapsed_time(e1), "b_part": tb["partition_ms"], "hist": tb["histogram_ms"], "scan": tb["scan_ms"],
