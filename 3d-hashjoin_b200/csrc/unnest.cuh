@@ -35,7 +35,7 @@ template <> __device__ __forceinline__ uint2 group_start_len<uint32_t>(const Gro
 // nested tuples come either as two columns (left[], gref[]) or as the (left, gref) pairs the nested probe wrote
 struct NestedIn {
   const uint32_t* left; const uint32_t* gref; const uint2* pairs;
-  __device__ __forceinline__ uint32_t g(uint64_t i) const { return pairs ? __ldg(&pairs[i].y) : __ldg(gref + i); }
+  __device__ __forceinline__ uint32_t g(uint64_t i) const { return pairs ? __ldg(pairs + i).y : __ldg(gref + i); }
   __device__ __forceinline__ uint2 lg(uint64_t i) const { return pairs ? __ldg(pairs + i) : make_uint2(__ldg(left + i), __ldg(gref + i)); }
 };
 
