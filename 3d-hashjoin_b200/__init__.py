@@ -8,6 +8,7 @@ The directory name is not an importable identifier; load it through ``hj3d_loade
 import ctypes as C
 
 from . import capi
+from . import sharding
 from .capi import (CHAINING, F_CHECKSUM, HASH_MURMUR32, HASH_MURMUR64, HASH_MURMUR64_SEXT32, NESTED, NO_ROWID,
                    OPT_PARTITION_BYTES, OPT_PARTITION_MIN_PROBE, OPT_PARTITION_WINDOW, OPT_SMEM_CHUNK, OPT_SMEM_MIN_PROBE,
                    OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_WARP_AGGREGATE, Counters, Hj3dError, KeySpec,

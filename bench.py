@@ -256,12 +256,7 @@ def run_ours(args):
         ev[0].record()
         counts = ctx.partition_by_owner(src, n, ks, D, world, base, part)
         ev[1].record()
-        sc = torch.tensor(counts, dtype=torch.int64, device=dev)
-        rc_ = torch.empty_like(sc)
-        dist.all_to_all_single(rc_, sc)
-        rcounts = rc_.tolist()
-        recv = torch.empty((sum(rcounts), 2), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(recv, part, output_split_sizes=rcounts, input_split_sizes=counts)
+        recv, _ = pkg.sharding.exchange_records(dist, part, counts, dev)
         ev[2].record()
         state.setdefault("xev", []).append(ev)
         state["shuffle_bytes"] = state.get("shuffle_bytes", 0) + 8 * (n - counts[rank])
