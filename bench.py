@@ -136,7 +136,8 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"main_experiment1 key/foreign-key join -R {args.log2_build} -S {args.log2_probe} --no-skew -t 0 -b 1, "
+    skew = "--no-skew" if args.zipf <= 0 else f"--skew (Zipf-like s={args.zipf}, device generated)"
+    return {"workload": f"main_experiment1 key/foreign-key join -R {args.log2_build} -S {args.log2_probe} {skew} -t 0 -b 1, "
                         f"plan {args.plan}, uint32 keys, 12-byte row-store tuples, materialised result pairs",
             "plan": args.plan, "log2_build": args.log2_build, "log2_probe": args.log2_probe,
             "l2_policy": "inputs (>= 1.6 GB + 12.9 GB) are far larger than the 126 MB L2; no flush needed",
@@ -211,7 +212,18 @@ def run_ours(args):
     g.manual_seed(99 + rank)
     S = torch.zeros((nSl, 3), dtype=torch.int32, device=dev)
     S[:, 0] = torch.arange(rank * nSl, (rank + 1) * nSl, device=dev, dtype=torch.int64).to(torch.int32)
-    S[:, 1] = torch.randint(0, nR, (nSl,), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+    if args.zipf > 0:   # Zipf-like foreign keys (config 4): inverse-CDF of a continuous power law, rank r ~ u^(1/(1-s)); NOT the
+        # libstdc++ bit stream of the reference's generator (device-side generation is for scale runs, never for parity)
+        u = torch.rand(nSl, device=dev, generator=g, dtype=torch.float64)
+        if abs(args.zipf - 1.0) < 1e-9:
+            rk = torch.exp(u * float(__import__("math").log(nR)))
+        else:
+            a = 1.0 - args.zipf
+            rk = (u * (float(nR) ** a - 1.0) + 1.0) ** (1.0 / a)
+        S[:, 1] = (rk.to(torch.int64) - 1).clamp_(0, nR - 1).to(torch.int32)
+        del u, rk
+    else:
+        S[:, 1] = torch.randint(0, nR, (nSl,), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
     ksRk, ksSa = pkg.KeySpec(12, 0), pkg.KeySpec(12, 4)
     B, ksB, nBl, P, ksP, nPl = (R, ksRk, nRl, S, ksSa, nSl) if build_rel == "R" else (S, ksSa, nSl, R, ksRk, nRl)
     nBg, nPg = (nR, nS) if build_rel == "R" else (nS, nR)
@@ -219,6 +231,8 @@ def run_ours(args):
         D = nR
     else:
         D = nR - int(nR * (1 - 1 / nR) ** nS) if nR > 1 else 1     # ~ #distinct S.a (numDvSa); any D is a valid table size
+        if args.zipf > 0:
+            D = max(int(torch.unique(S[:, 1]).numel()), 1)             # numDvSa of the skewed column (N=1 only)
     ks_rec = pkg.KeySpec(8, 0, 4, 0, 4)
     lib = pkg.capi.load()
     if world > 1:
@@ -453,6 +467,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the nested plan (N=1)")
+    ap.add_argument("--zipf", type=float, default=0.0, help="skew of the foreign keys S.a (0 = uniform; config 4 uses 0.5 .. 1.5)")
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (HJ3D_OPT_*), repeatable")
