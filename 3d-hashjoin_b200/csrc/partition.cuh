@@ -111,7 +111,13 @@ __global__ void k_part_fixed_starts(uint32_t n_parts, unsigned long long cap, un
 // build-side row id + rowid_base.  Records of buckets outside the directory (q >= n_parts) are dropped.
 // Tile shape: THREADS threads x (64 / sizeof(Slot)) records per thread * 2, i.e. 16 records per thread for
 // 8-byte slots, 8 for 16-byte slots.
-template <class KeyT> struct PartCfg { static constexpr int kItems = 128 / (int)sizeof(Slot<KeyT>); };
+#ifndef HJ3D_PART_TILE_BYTES
+#define HJ3D_PART_TILE_BYTES 128
+#endif
+#ifndef HJ3D_PART_MINBLOCKS
+#define HJ3D_PART_MINBLOCKS 1
+#endif
+template <class KeyT> struct PartCfg { static constexpr int kItems = HJ3D_PART_TILE_BYTES / (int)sizeof(Slot<KeyT>); };
 
 // dynamic shared memory: sorted tile + partition id per record + (dst, hist, loff, klim) per local
 // partition + one private histogram per warp (RANK_MATCH)
@@ -127,7 +133,7 @@ template <class KeyT> inline size_t part_smem_bytes(uint32_t fan, int threads, b
 // RANK_MATCH = true : every warp owns a private histogram; lanes with the same partition are found with
 //                     __match_any_sync and the group's leader bumps the counter with a plain load/store.
 template <int HASH, bool LEFTID, bool RECS, int THREADS, bool RANK_MATCH>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS <= 512 ? HJ3D_PART_MINBLOCKS : 1)
 k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint32_t n_parts, uint32_t fan,
                uint32_t rowid_base, unsigned long long cap,
                const unsigned long long* __restrict__ part_start, unsigned long long* __restrict__ cursor,

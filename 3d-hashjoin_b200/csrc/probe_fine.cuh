@@ -7,10 +7,10 @@
 // side to be ISSUE bound, not HBM bound (~350 warp instructions per 32 probe records over the three
 // passes, 50-68 % issue-slot utilisation), so this kernel is written for few instructions per record:
 //   * 32-bit indexing inside the work item, full tiles take an unguarded path;
-//   * the next tile's records are loaded (8 x LDG.64 per thread) before the current tile is probed, so no
+//   * the next tile's records are loaded (one LDG.64 per record) before the current tile is probed, so no
 //     warp ever waits on a just-issued global load;
 //   * results are counted with warp ballots and placed with ONE shared-memory word per warp and ONE global
-//     atomic per 2048 probe records (no 64-bit block scan);
+//     atomic per tile of 1024 probe records (no 64-bit block scan);
 //   * the per-thread counters are 32 bit inside a tile and folded into 64 bit once per tile;
 //   * long (> kOrderedMax) buckets, which need the row-id based rules of probe.cuh, are out of line.
 #pragma once
@@ -21,8 +21,17 @@
 
 namespace hj3d {
 
+// Tile shape, measured at 2^27 x 2^30 (probe kernel ms): 8 items / 80 registers / 3 blocks per SM 6.21; 8 items / 64
+// registers / 4 blocks 5.61; 4 items / 48 registers / 5 blocks 5.39; 4 items / 40 registers / 6 blocks 6.63 (spills).
+// The kernel is latency bound (issue slots 56 % busy), so resident warps beat items per thread.
+#ifndef HJ3D_FINE_ITEMS
+#define HJ3D_FINE_ITEMS 4
+#endif
+#ifndef HJ3D_FINE_MINBLOCKS
+#define HJ3D_FINE_MINBLOCKS 5
+#endif
 constexpr int kFineThreads = 256;
-constexpr int kFineItems   = 8;
+constexpr int kFineItems   = HJ3D_FINE_ITEMS;
 constexpr int kFineTile    = kFineThreads * kFineItems;
 
 // ---- out-of-line rules for buckets longer than kOrderedMax (unordered storage) -------------------
@@ -160,7 +169,7 @@ __device__ __forceinline__ void probe_fine_items(const Slot<typename HashT<HASH>
 
 // KIND 0: chaining probe with IsBuildKeyUnique over (off, Slot rows); KIND 1: nested probe over (goff, Group rows).
 template <int HASH, int KIND, bool CHECKSUM, bool WRITE>
-__global__ void __launch_bounds__(kFineThreads)
+__global__ void __launch_bounds__(kFineThreads, HJ3D_FINE_MINBLOCKS)
 k_probe_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs, Dir d, FineCfg fc, const uint2* __restrict__ work,
              const uint32_t* __restrict__ work_part, const uint32_t* __restrict__ off, const void* __restrict__ rows_v,
              uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {

@@ -42,35 +42,45 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region: one streaming nvidia-smi (-lms 50) whose lines are
+    time stamped; summary() keeps the samples that fall inside [t_begin, t_end] (the timed steps) and says how many of
+    the surrounding warm-up samples it had to add when the timed region was shorter than a few sampling periods."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append((time.perf_counter(), f))
+        except Exception:
+            pass
 
     def summary(self):
-        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()                     # the exact process we started
         self.join(timeout=6)
-        if not self.samples:
+        inside = [f for t, f in self.samples if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t)]
+        used, extra = inside, 0
+        if len(inside) < 3:                           # a ~100 ms timed region: add the warm-up samples (same load) around it
+            used = [f for _, f in self.samples]
+            extra = len(used) - len(inside)
+        if not used:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(float(s[0])) for s in self.samples)
+        sm = sorted(int(float(f[0])) for f in used)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(f[3 + i].lower().startswith("active") for f in used)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(used[0][1])), "reasons": reasons,
+                "samples": len(used), "samples_in_timed_region": len(inside), "samples_from_warmup": extra,
+                "power_w_max": max(float(f[2]) for f in used)}
 
 
 def algorithmic_bytes(nB, nP, nM, nO, D, T=12, K=4, I=4, nested=False):
@@ -315,22 +325,26 @@ def run_ours(args):
         flags = flags_keep
         verified = bool(res0["checksum_sum"] == expected_checksum_sum() and res0["out_tuples"] == nS)
         assert verified, "full-size result checksum differs from the independent torch computation"
-    for _ in range(args.warmup):
-        step()
-    sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sync_all()
     launches0 = ctx.timings()["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     probe_ms, build_ms = [], []
     sync_all()
+    if sampler:
+        sampler.t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         res = step()
         probe_ms.append(state["probe"]["probe_ms"]); build_ms.append(state["build"]["total_ms"])
     e1.record()
     sync_all()
+    if sampler:
+        sampler.t_end = time.perf_counter()
     ms = e0.elapsed_time(e1) / args.steps
     launches = ctx.timings()["kernel_launches"] - launches0
     clocks = sampler.summary() if sampler else None
