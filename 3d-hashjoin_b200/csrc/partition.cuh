@@ -115,7 +115,7 @@ __global__ void k_part_fixed_starts(uint32_t n_parts, unsigned long long cap, un
 #define HJ3D_PART_TILE_BYTES 128
 #endif
 #ifndef HJ3D_PART_MINBLOCKS
-#define HJ3D_PART_MINBLOCKS 1
+#define HJ3D_PART_MINBLOCKS 2
 #endif
 template <class KeyT> struct PartCfg { static constexpr int kItems = HJ3D_PART_TILE_BYTES / (int)sizeof(Slot<KeyT>); };
 

@@ -434,15 +434,24 @@ def run_ours(args):
     n_res = res["out_tuples"] if not nested_plan else state["probe_counters"]["matches"]
     table_bytes = 4 * (D // world) + (nBg // world) * 8 if not nested_plan else 4 * (D // world) + 16 * min(nBg, D) // world
     probe_bytes = state["n_probe_local"] * 8 + n_res * 8 + table_bytes
+    kernel_name = {1: "k_probe_fine<chaining, IsBuildKeyUnique>", 0: "k_probe_chaining_smem", 3: "k_probe_fine<nested>"}[mode]
+    traffic = None                                   # from the committed ncu capture of this kernel at this configuration, if any
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel_name)
+        if tj and (tj["plan"], tj["log2_build"], tj["log2_probe"], tj["n_gpus"]) == (args.plan, args.log2_build, args.log2_probe, world) \
+                and args.zipf <= 0:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {"metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e if e2e is not None else {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                                "note": "e2e is measured at N=1"},
-            "roofline": {"bound": "hbm", "kernel": {1: "k_probe_fine<chaining, IsBuildKeyUnique>", 0: "k_probe_chaining_smem", 3: "k_probe_fine<nested>"}[mode],
+            "roofline": {"bound": "hbm", "kernel": kernel_name,
                          "achieved": probe_bytes / (pm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": probe_bytes / (pm * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": probe_bytes / (pm * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": pm, "algorithmic_bytes_per_launch": probe_bytes,
                          "join_algorithmic_bytes": alg, "join_frac": alg / (ms * 1e-3) / 1e9 / peak / world},
             "phases_ms": {"build_total": sum(build_ms) / len(build_ms), "histogram": state["build"]["histogram_ms"],
