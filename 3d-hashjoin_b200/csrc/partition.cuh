@@ -162,13 +162,28 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   // ---- load the tile's keys (and ids): all loads are issued before the first use
   KeyT     key[ITEMS];
   uint32_t id[ITEMS];
-  if (RECS) {
+  // (ncu: the generic loads below -- 64-bit index arithmetic, gather / row-id checks and a bounds check per tuple -- were
+  //  31 % of the level-1 kernel's instructions; full tiles of a plain row store take the short paths)
+  if (RECS && tn == (uint32_t)TILE) {
+    const SlotT* in = reinterpret_cast<const SlotT*>(s.base) + t0 + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) { const SlotT r = in[j * THREADS]; key[j] = r.key; id[j] = r.rowid; }
+  } else if (RECS) {
     const SlotT* in = reinterpret_cast<const SlotT*>(s.base) + t0;
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
       const uint32_t li = j * THREADS + threadIdx.x;
       key[j] = 0; id[j] = 0;
       if (li < tn) { const SlotT r = in[li]; key[j] = r.key; id[j] = r.rowid; }
+    }
+  } else if (!s.gather && s.rowid_off == HJ3D_NO_ROWID && tn == (uint32_t)TILE) {
+    const uint8_t* p0 = s.base + (t0 + threadIdx.x) * (uint64_t)s.stride + s.key_off;
+    const uint32_t step = (uint32_t)THREADS * s.stride;
+    const uint32_t id0 = (uint32_t)t0 + threadIdx.x + (LEFTID ? 0u : rowid_base);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      key[j] = __ldg(reinterpret_cast<const KeyT*>(p0 + (size_t)((uint32_t)j * step)));
+      id[j] = id0 + (uint32_t)j * THREADS;
     }
   } else {
 #pragma unroll
@@ -190,13 +205,16 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
 
   // ---- rank every record inside its partition of this tile
   uint32_t pr[ITEMS];                               // (local partition << 16) | rank, 0xFFFFFFFF = dropped
+  // the partition of a key: generic (exact fast-mod bucket, division by the range width) or, when the directory size and
+  // the range width are powers of two (the reference's -R / -b 1 shapes), a mask and a shift
+  auto rank_all = [&](auto part_of) {
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t li = j * THREADS + threadIdx.x;
     pr[j] = 0xFFFFFFFFu;
     uint32_t lp = 0xFFFFFFFFu;
     if (li < tn) {
-      const uint32_t q = pf(HashT<HASH>::bucket(key[j], d));
+      const uint32_t q = part_of(key[j]);
       if (q < n_parts && q - q0 < fan) lp = q - q0;
     }
     if (RANK_MATCH) {
@@ -222,6 +240,9 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
       if (lp != 0xFFFFFFFFu) pr[j] = (lp << 16) | atomicAdd(&hist[lp], 1u);
     }
   }
+  };
+  if (d.is_pow2 && pf.is_pow2) rank_all([&](KeyT k) { return ((HashT<HASH>::hash_lo32(k) & d.pow2_mask) - pf.lo) >> pf.shift; });
+  else                         rank_all([&](KeyT k) { return pf(HashT<HASH>::bucket(k, d)); });
   __syncthreads();
   if (RANK_MATCH) {  // per partition: warp counts -> exclusive prefix over warps (each warp's base), total -> hist
     for (uint32_t p = threadIdx.x; p < fan; p += THREADS) {
@@ -267,6 +288,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   __syncthreads();
   // ---- coalesced write-out: consecutive threads store consecutive records of a run
   const uint32_t kept = loff[fan - 1] + hist[fan - 1];
+  // (a 32-bit index variant of this loop with a no-overflow fast path measured 0.5 ms SLOWER per 2^30 records)
   for (uint32_t k = threadIdx.x; k < kept; k += THREADS) {
     const uint32_t lp = pid[k];
     if (k < klim[lp]) out[dst[lp] + k] = tile[k];
