@@ -233,10 +233,6 @@ struct StoreCells {
 struct LoadDiff { const uint32_t* p; __device__ uint32_t operator()(uint64_t i) const { return p[i + 1] - p[i]; } };
 struct StoreNone { __device__ void operator()(uint64_t, uint32_t, uint32_t) const {} };
 
-template <class KeyT> struct LoadGroupLen {
-  const Group<KeyT>* groups; const uint32_t* gref; uint64_t n;
-  __device__ unsigned long long operator()(uint64_t i) const { return i < n ? (unsigned long long)groups[gref[i]].len : 0ull; }
-};
 struct LoadU64 { const unsigned long long* p; __device__ unsigned long long operator()(uint64_t i) const { return p[i]; } };
 struct StoreExU64 { unsigned long long* p; __device__ void operator()(uint64_t i, unsigned long long ex, unsigned long long) const { p[i] = ex; } };
 
@@ -978,52 +974,40 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   const NestedIn in{left, gref, pairs};
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
-  unsigned long long total = 0;
-  unsigned long long* h = (unsigned long long*)c->h_pinned;
-  // warp-cooperative expansion (unnest.cuh): per-block sums -> scan -> expand
+  // single pass (unnest.cuh): every block reserves its output range on d_ctr->out_cursor; hot tuples are listed and
+  // expanded by k_unnest_hot; if the list overflows (pathological skew) the pass is repeated with a list of n entries
   const uint32_t nb = blocks_for(n, kUxTile);
-  unsigned long long *sums = nullptr, *bases = nullptr;
-  HJ_TRY(dev_alloc(c, &sums, (uint64_t)nb + 1));
-  HJ_TRY(dev_alloc(c, &bases, (uint64_t)nb + 1));
-  CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 16, c->stream));
-  if (nb) {
-    k_unnest_count<KeyT><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, sums, c->d_scalar + 1);
-    ++c->launches;
-  }
-  if (nb) HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{sums}, StoreExU64{bases}, nb, (DevStats*)nullptr, c->d_scalar)));
-  CUDA_TRY(cudaMemcpyAsync(h, c->d_scalar, 16, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  total = nb ? h[0] : 0;
-  const bool hot = h[1] > kUnnestWarpMax;                  // a group too long for one warp: element-balanced kernel
-  if (total && (cs || wr) && !hot) {
-#define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, t->rows, bases, out, cap, c->d_ctr)
+  uint32_t hot_cap = 1u << 20;
+  DevCounters* hc = (DevCounters*)c->h_pinned;
+  unsigned long long* h_hot = (unsigned long long*)((char*)c->h_pinned + 512);
+  for (int attempt = 0; attempt < 2 && nb; ++attempt) {
+    uint32_t* hot_list = nullptr;
+    HJ_TRY(dev_alloc(c, &hot_list, hot_cap));
+    CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 8, c->stream));
+    if (attempt) CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+#define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, t->rows, out, cap, c->d_ctr, hot_list, hot_cap, c->d_scalar)
     if (cs) { if (wr) LAUNCH_UX(true, true); else LAUNCH_UX(true, false); }
-    else    { LAUNCH_UX(false, true); }
+    else    { if (wr) LAUNCH_UX(false, true); else LAUNCH_UX(false, false); }
 #undef LAUNCH_UX
     ++c->launches;
-  } else if (total && (cs || wr)) {
-    if (pairs) {                                           // the element-balanced kernel reads two columns
-      uint32_t *l2 = nullptr, *g2 = nullptr;
-      HJ_TRY(dev_alloc(c, &l2, n)); HJ_TRY(dev_alloc(c, &g2, n));
-      k_split_pairs<<<blocks_for(n, 256), 256, 0, c->stream>>>(pairs, n, l2, g2);
+    CUDA_TRY(cudaMemcpyAsync(h_hot, c->d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const unsigned long long n_hot = *h_hot;
+    if (n_hot > hot_cap) { hot_cap = (uint32_t)n; continue; }             // list overflow: once more with room for every tuple
+    if (n_hot) {
+      const uint32_t nbh = n_hot < 4096 ? (uint32_t)n_hot : 4096u;
+#define LAUNCH_UH(C, W) k_unnest_hot<KeyT, C, W><<<nbh, kUxThreads, 0, c->stream>>>(in, hot_list, (uint32_t)n_hot, groups, t->rows, out, cap, c->d_ctr)
+      if (cs) { if (wr) LAUNCH_UH(true, true); else LAUNCH_UH(true, false); }
+      else    { if (wr) LAUNCH_UH(false, true); else LAUNCH_UH(false, false); }
+#undef LAUNCH_UH
       ++c->launches;
-      left = l2; gref = g2;
     }
-    unsigned long long* offsets = nullptr;
-    HJ_TRY(dev_alloc(c, &offsets, n + 1));
-    HJ_TRY((run_scan<unsigned long long, false>(c, LoadGroupLen<KeyT>{groups, gref, n}, StoreExU64{offsets}, n + 1,
-                                                  (DevStats*)nullptr, c->d_scalar)));
-    const uint32_t nbe = (uint32_t)((total + kUnnestTile - 1) / kUnnestTile);
-#define LAUNCH_UN(C, W) k_unnest<KeyT, C, W><<<nbe, kUnnestThreads, 0, c->stream>>>(left, gref, n, offsets, groups, t->rows, out, cap, c->d_ctr)
-    if (cs) { if (wr) LAUNCH_UN(true, true); else LAUNCH_UN(true, false); }
-    else    { LAUNCH_UN(false, true); }
-#undef LAUNCH_UN
-    ++c->launches;
+    break;
   }
-  DevCounters* hc = (DevCounters*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(hc, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
+  const unsigned long long total = nb ? hc->out_cursor : 0ull;
   res->matches = total; res->out_tuples = total; res->num_cmps = 0;     // AlgUnnestHt::_count = #outputs (algebra.hh:486-487)
   res->checksum_sum = hc->checksum_sum; res->checksum_xor = hc->checksum_xor;
   res->overflow = (wr && total > cap) ? 1 : 0;

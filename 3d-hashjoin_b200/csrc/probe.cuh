@@ -1,4 +1,4 @@
-// probe.cuh -- probe-side kernels: chaining probe, nested probe, deferred unnest.
+// probe.cuh -- probe-side kernels: chaining probe, nested probe (the deferred unnest lives in unnest.cuh).
 //
 // Every probe thread recomputes the counters the reference accumulates tuple-at-a-time:
 //   matches  = AlgBase::_count of the probe operator,  num_cmps = _numCmps (algebra.hh:449,658).
@@ -249,64 +249,6 @@ k_probe_nested(Src s, Dir d, const uint2* __restrict__ tilemap, const uint32_t* 
   probe_nested_tile<KeyT, CHECKSUM, WRITE, RECS, kProbeThreads, kProbeItems, HASH>(
       s, d, t0, tn, d.lo, d.n_local, goff, 0u, groups, out, out_cap, ctr, acc, sm_scan, &sm_base);
   commit_acc(acc, ctr, CHECKSUM);
-}
-
-// ---- deferred unnest ------------------------------------------------------------------------------
-// offsets[i] (exclusive scan of group lengths, n+1 entries) -> load-balanced expansion: every block
-// produces kUnnestTile consecutive outputs, locating their source nested tuples by binary search.
-constexpr int kUnnestThreads = 256;
-constexpr int kUnnestItems   = 8;
-constexpr int kUnnestTile    = kUnnestThreads * kUnnestItems;
-constexpr int kUnnestSrcCap  = 2048;
-
-__device__ __forceinline__ uint64_t upper_bound_u64(const unsigned long long* a, uint64_t n, unsigned long long v) {
-  uint64_t lo = 0, hi = n;       // first index with a[idx] > v
-  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-
-template <class KeyT, bool CHECKSUM, bool WRITE>
-__global__ void __launch_bounds__(kUnnestThreads)
-k_unnest(const uint32_t* __restrict__ left, const uint32_t* __restrict__ gref, uint64_t n,
-         const unsigned long long* __restrict__ offsets /* n+1 */,
-         const Group<KeyT>* __restrict__ groups, const uint32_t* __restrict__ rows,
-         uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
-  __shared__ unsigned long long sm_off[kUnnestSrcCap + 1];
-  __shared__ uint64_t sm_s0, sm_s1;
-  const unsigned long long total = offsets[n];
-  const unsigned long long t0 = (unsigned long long)blockIdx.x * kUnnestTile;
-  if (t0 >= total) return;
-  const unsigned long long t1 = (t0 + kUnnestTile < total) ? t0 + kUnnestTile : total;
-  if (threadIdx.x == 0) sm_s0 = upper_bound_u64(offsets, n + 1, t0) - 1;       // source of output t0
-  if (threadIdx.x == 32) sm_s1 = upper_bound_u64(offsets, n + 1, t1 - 1) - 1;  // source of output t1-1
-  __syncthreads();
-  const uint64_t s0 = sm_s0, s1 = sm_s1;
-  const bool staged = (s1 - s0 + 1) <= (uint64_t)kUnnestSrcCap;
-  if (staged) {
-    for (uint64_t k = threadIdx.x; k <= s1 - s0 + 1; k += kUnnestThreads) sm_off[k] = offsets[s0 + k];
-    __syncthreads();
-  }
-  ProbeAcc acc;
-#pragma unroll
-  for (int j = 0; j < kUnnestItems; ++j) {
-    const unsigned long long o = t0 + threadIdx.x + (unsigned long long)j * kUnnestThreads;
-    if (o >= t1) continue;
-    uint64_t src;
-    unsigned long long src_off;
-    if (staged) {
-      uint64_t k = upper_bound_u64(sm_off, s1 - s0 + 2, o) - 1;
-      src = s0 + k; src_off = sm_off[k];
-    } else {
-      src = s0 + upper_bound_u64(offsets + s0, s1 - s0 + 2, o) - 1;
-      src_off = offsets[src];
-    }
-    const Group<KeyT> g = groups[gref[src]];
-    const uint32_t row = rows[g.start + (uint32_t)(o - src_off)];
-    const uint32_t l = left[src];
-    if (CHECKSUM) { const uint64_t mx = pair_mix(l, row); acc.sum += mx; acc.x ^= mx; }
-    if (WRITE && o < out_cap) out[o] = make_uint2(l, row);
-  }
-  if (CHECKSUM) commit_acc(acc, ctr, true);
 }
 
 // ---- small column helpers -------------------------------------------------------------------------

@@ -169,7 +169,8 @@ __device__ __forceinline__ void probe_fine_items(const Slot<typename HashT<HASH>
 
 // KIND 0: chaining probe with IsBuildKeyUnique over (off, Slot rows); KIND 1: nested probe over (goff, Group rows).
 template <int HASH, int KIND, bool CHECKSUM, bool WRITE>
-__global__ void __launch_bounds__(kFineThreads, HJ3D_FINE_MINBLOCKS)
+// (the nested variant walks 16-byte group records and spills at 48 registers: 8.5 ms; 4 blocks / 64 registers suit it)
+__global__ void __launch_bounds__(kFineThreads, KIND == 0 ? HJ3D_FINE_MINBLOCKS : HJ3D_FINE_MINBLOCKS - 1)
 k_probe_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs, Dir d, FineCfg fc, const uint2* __restrict__ work,
              const uint32_t* __restrict__ work_part, const uint32_t* __restrict__ off, const void* __restrict__ rows_v,
              uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
