@@ -266,11 +266,14 @@ k_order_groups(const uint32_t* __restrict__ goff, Group<KeyT>* __restrict__ grou
 // statistics of makeStatistics are reduced on the way.  base[f] = number of build records in
 // partitions < f.  A partition with more than `cap_recs` records sets *overflow and is skipped (the
 // caller then rebuilds with the global-memory kernels).
-constexpr int kFineBuildThreads = 256;   // ~95 registers: 512-thread blocks fit one per SM, 256-thread blocks two or more
+constexpr int kFineBuildThreads = 256;   // latency bound: resident warps matter more than registers per thread
 constexpr int kFineBuildItems   = 12;
 
 template <int HASH>
-__global__ void __launch_bounds__(kFineBuildThreads, 2)
+#ifndef HJ3D_BUILD_MINBLOCKS
+#define HJ3D_BUILD_MINBLOCKS 4   // measured at 2^27 rows: 2 blocks (121 regs) 2.34 ms, 3 blocks (80) 1.84, 4 blocks (64, small spills) 1.72
+#endif
+__global__ void __launch_bounds__(kFineBuildThreads, HJ3D_BUILD_MINBLOCKS)
 k_build_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
              const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
              const unsigned long long* __restrict__ base, Dir d, uint32_t width, uint32_t n_fine, uint32_t cap_recs,

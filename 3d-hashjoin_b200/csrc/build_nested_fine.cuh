@@ -40,7 +40,7 @@ __device__ __forceinline__ bool rec_less(const Slot<KeyT>& a, const Slot<KeyT>& 
 }
 
 template <int HASH>
-__global__ void __launch_bounds__(kNfThreads, 2)
+__global__ void __launch_bounds__(kNfThreads, 4)
 k_build_fine_nested(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
                     const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
                     const unsigned long long* __restrict__ base, Dir d, uint32_t width, uint32_t n_fine, uint32_t cap_recs,
@@ -111,29 +111,26 @@ k_build_fine_nested(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
   }
   __syncthreads();
   // ---- 2. rank inside the bucket by (key, row id); leaders (smallest row id of their key) count the distinct keys
-  // info = leader << 31 | group length << 14 | rank            (records of thread t: t, t + kNfThreads, ...)
-  uint32_t info[kNfItems], my_b[kNfItems];
+  // info = leader << 31 | local bucket << 14 | rank            (records of thread t: t, t + kNfThreads, ...)
+  uint32_t info[kNfItems];
 #pragma unroll
   for (int j = 0; j < kNfItems; ++j) {
     const uint32_t i = j * kNfThreads + threadIdx.x;
-    info[j] = 0; my_b[j] = 0;
+    info[j] = 0;
     if (i >= cnt) continue;
     const SlotT me = srec[i];
     const uint32_t b = HashT<HASH>::bucket(me.key, d) - d.lo - blo;
     const uint32_t lo = sm_cnt[b], hi = sm_cnt[b + 1];
-    uint32_t less = 0, same = 0, same_before = 0;
+    uint32_t less = 0, same_before = 0;
     for (uint32_t q = lo; q < hi; ++q) {
       const SlotT o = srec[q];
-      const bool eq = o.key == me.key;
       less += (o.key < me.key) ? 1u : 0u;
-      same += eq ? 1u : 0u;
-      same_before += (eq && o.rowid < me.rowid) ? 1u : 0u;
+      same_before += (o.key == me.key && o.rowid < me.rowid) ? 1u : 0u;
     }
     const uint32_t leader = same_before == 0 ? 1u : 0u;
     if (leader) atomicAdd(&sm_dk[b], 1u);
     sm_flag[i] = (unsigned char)leader;
-    info[j] = (leader << 31) | (same << 14) | (less + same_before);
-    my_b[j] = b;
+    info[j] = (leader << 31) | (b << 14) | (less + same_before);
   }
   __syncthreads();
   // ---- 3. statistics over the main chain lengths + exclusive scan, first global group index by look-back
@@ -197,14 +194,18 @@ k_build_fine_nested(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs,
     const uint32_t i = j * kNfThreads + threadIdx.x;
     if (i >= cnt) continue;
     const SlotT me = srec[i];
-    const uint32_t b = my_b[j];
+    const uint32_t b = (info[j] >> 14) & 0x1FFFFu;
     const uint32_t lo = sm_cnt[b], hi = sm_cnt[b + 1];
     const uint32_t pos = rbase + lo + (info[j] & 0x3FFFu);
     rows[pos] = me.rowid;
     if (info[j] >> 31) {
-      uint32_t gi = 0;                                                       // leaders of this bucket inserted before me
-      for (uint32_t q = lo; q < hi; ++q) gi += (sm_flag[q] && srec[q].rowid < me.rowid) ? 1u : 0u;
-      GroupT g; g.key = me.key; g.first_row = me.rowid; g.start = pos; g.len = (info[j] >> 14) & 0x1FFFFu;
+      uint32_t gi = 0, len = 0;                                              // leaders of this bucket inserted before me; my group's length
+      for (uint32_t q = lo; q < hi; ++q) {
+        const SlotT o = srec[q];
+        gi += (sm_flag[q] && o.rowid < me.rowid) ? 1u : 0u;
+        len += o.key == me.key ? 1u : 0u;
+      }
+      GroupT g; g.key = me.key; g.first_row = me.rowid; g.start = pos; g.len = len;
       groups[gbase + sm_dk[b] + gi] = g;
     }
   }
