@@ -196,12 +196,17 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
       }
     }
   }
-  if (threadIdx.x == 0) {
-    const uint32_t q = tn ? pf(HashT<HASH>::bucket(key[0], d)) : 0u;
-    sm_q0 = q < n_parts ? (q / fan) * fan : 0u;
+  uint32_t q0 = 0;
+  if (n_parts > fan) {                               // level 2: the tile's coarse partition = fan consecutive fine ones from q0 on
+    if (threadIdx.x == 0) {
+      const uint32_t q = tn ? pf(HashT<HASH>::bucket(key[0], d)) : 0u;
+      sm_q0 = q < n_parts ? (q / fan) * fan : 0u;
+    }
+    __syncthreads();
+    q0 = sm_q0;
+  } else {
+    __syncthreads();                                 // the zeroed histogram is visible
   }
-  __syncthreads();
-  const uint32_t q0 = sm_q0;
 
   // ---- rank every record inside its partition of this tile
   uint32_t pr[ITEMS];                               // (local partition << 16) | rank, 0xFFFFFFFF = dropped
@@ -260,8 +265,17 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
     uint32_t v[PER], sum = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) { v[k] = (a + k) < fan ? hist[a + k] : 0u; sum += v[k]; }
-    uint32_t tot;
-    uint32_t ex = block_exscan(sum, sm_scan, &tot);
+    // block-wide exclusive scan of `sum` (sm_scan is used once per block: no trailing barrier needed)
+    uint32_t ex;
+    {
+      const uint32_t w = threadIdx.x >> 5, l = lane_id();
+      const uint32_t inc = warp_iscan(sum);
+      if (l == 31) sm_scan[w] = inc;
+      __syncthreads();
+      if (w == 0) { const uint32_t t = l < (uint32_t)WARPS ? sm_scan[l] : 0u; const uint32_t ti = warp_iscan(t); sm_scan[l] = ti - t; }
+      __syncthreads();
+      ex = inc - sum + sm_scan[w];
+    }
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       if ((a + k) < fan) {
