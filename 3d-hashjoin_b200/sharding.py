@@ -23,6 +23,26 @@ def exchange_records(dist, part, counts, device):
     return recv, rcounts
 
 
+def exchange_many(dist, parts, counts_list, device, recv_bufs=None):
+    """The same exchange for several relations at once: ONE small collective carries the counts of all of them (one host
+    synchronisation instead of one per relation), then one all-to-all-v per relation into `recv_bufs` (optional
+    preallocated [capacity, 2] int32 buffers; a fresh tensor is used when the capacity does not suffice).
+    Returns [(received records, received counts), ...]."""
+    k = len(parts)
+    sc = torch.tensor(counts_list, dtype=torch.int64, device=device).t().contiguous()      # [world, k]: row g goes to rank g
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    rcounts = [[int(x) for x in col] for col in rc.t().tolist()]
+    out = []
+    for i in range(k):
+        need = sum(rcounts[i])
+        buf = recv_bufs[i] if recv_bufs is not None and recv_bufs[i] is not None and recv_bufs[i].shape[0] >= need else None
+        recv = buf[:need] if buf is not None else torch.empty((need, 2), dtype=torch.int32, device=device)
+        dist.all_to_all_single(recv, parts[i], output_split_sizes=rcounts[i], input_split_sizes=[int(x) for x in counts_list[i]])
+        out.append((recv, rcounts[i]))
+    return out
+
+
 def merge_counters(dist, c, device):
     """Counters of the sharded join = counters of the unsharded one: sums (checksum_sum modulo 2^64), xor of checksum_xor."""
     world = dist.get_world_size()

@@ -61,15 +61,23 @@ def worker(rank, world, port, nR, nS, D, mode, q):
         width = (D + world - 1) // world
         assert lo_.value == min(rank * width, D) and hi_.value == min((rank + 1) * width, D)
         nRl, nSl = nR // world, nS // world
-        mine = {}
-        for name, rel, col, nl in (("B", R, 0, nRl), ("P", S, 1, nSl)):
+        parts, counts = [], []
+        for rel, col, nl in ((R, 0, nRl), (S, 1, nSl)):
             sl = rel[rank * nl:(rank + 1) * nl]
-            recs, counts = partition_by_owner_np(sl[:, col], rank * nl, D, width, world)
-            recv, rcounts = pkg.sharding.exchange_records(dist, torch.from_numpy(recs.view(np.int32)), counts, dev)
-            got = recv.numpy().view(np.uint32)
-            b = murmur32_np(got[:, 0]) % np.uint32(D)
+            recs, cnt = partition_by_owner_np(sl[:, col], rank * nl, D, width, world)
+            parts.append(torch.from_numpy(recs.view(np.int32))); counts.append(cnt)
+        # both relations through one exchange (one counts collective), as bench.py --gpus N does; the build side once more
+        # through the single-relation call: same records
+        got = pkg.sharding.exchange_many(dist, parts, counts, dev, [None, torch.empty((nSl * 2, 2), dtype=torch.int32)])
+        again, _ = pkg.sharding.exchange_records(dist, parts[0], counts[0], dev)
+        assert torch.equal(again, got[0][0])
+        mine = {}
+        for name, (recv, rcounts) in zip(("B", "P"), got):
+            arr = np.ascontiguousarray(recv.numpy().view(np.uint32))
+            assert len(arr) == sum(rcounts)
+            b = murmur32_np(arr[:, 0]) % np.uint32(D)
             assert np.all((b >= lo_.value) & (b < hi_.value)), "a record reached a rank that does not own its bucket"
-            mine[name] = np.ascontiguousarray(got)
+            mine[name] = arr
         orc = pyo.Oracle()
         ks = pyo.KeySpec(8, 0, 4, 0, 4)
         kind = pyo.CHAINING if mode == 1 else pyo.NESTED
