@@ -62,6 +62,7 @@ struct hj3d_ctx {
   int64_t cluster_min_probe = 1ll << 22;    // smaller probe inputs use the other paths
   int64_t cluster_min_parts = 64;           // coarse partitions needed to keep every cluster busy
   int64_t cluster_slice_bytes = 0;          // > 0: cap on the slice's shared memory (tests)
+  int64_t unnest_hot_cap = 1ll << 20;       // entries of the unnest's hot-tuple list before it is re-run with room for all
   int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
   int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // per-phase events of the last call
@@ -977,12 +978,12 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   // single pass (unnest.cuh): every block reserves its output range on d_ctr->out_cursor; hot tuples are listed and
   // expanded by k_unnest_hot; if the list overflows (pathological skew) the pass is repeated with a list of n entries
   const uint32_t nb = blocks_for(n, kUxTile);
-  uint32_t hot_cap = 1u << 20;
+  uint32_t hot_cap = (uint32_t)c->unnest_hot_cap;
   DevCounters* hc = (DevCounters*)c->h_pinned;
   unsigned long long* h_hot = (unsigned long long*)((char*)c->h_pinned + 512);
   for (int attempt = 0; attempt < 2 && nb; ++attempt) {
     uint32_t* hot_list = nullptr;
-    HJ_TRY(dev_alloc(c, &hot_list, hot_cap));
+    HJ_TRY(dev_alloc(c, &hot_list, hot_cap ? hot_cap : 1u));
     CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 8, c->stream));
     if (attempt) CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
 #define LAUNCH_UX(C, W) k_unnest_expand<KeyT, C, W><<<nb, kUxThreads, 0, c->stream>>>(in, n, groups, t->rows, out, cap, c->d_ctr, hot_list, hot_cap, c->d_scalar)
@@ -1107,6 +1108,7 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_CLUSTER_MIN_PROBE: c->cluster_min_probe = v; break;
     case HJ3D_OPT_CLUSTER_MIN_PARTS: if (v >= 1) c->cluster_min_parts = v; break;
     case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
+    case HJ3D_OPT_UNNEST_HOT_CAP: if (v >= 0 && v <= (1ll << 30)) c->unnest_hot_cap = v; break;
     case HJ3D_OPT_CLUSTER_SLICE_BYTES: c->cluster_slice_bytes = v > 0 ? (v & ~15ll) : 0; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }

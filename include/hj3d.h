@@ -70,6 +70,7 @@ extern "C" {
 #define HJ3D_OPT_CLUSTER_MIN_PARTS 16 /* coarse partitions needed before the cluster probe is used (default 64)    */
 #define HJ3D_OPT_CLUSTER_SLICE_BYTES 17 /* cap on the shared memory used for a CTA's table slice (default: all there is) */
 #define HJ3D_OPT_LEAN_PROBE      18 /* 0/1: unique / nested probes of fine partitions use the lean kernel (default 1)  */
+#define HJ3D_OPT_UNNEST_HOT_CAP  19 /* entries of the unnest's hot-tuple list (default 2^20; tests shrink it)           */
 #define HJ3D_OPT_PART_RANK_MATCH 10 /* 0: rank by shared-memory atomics (default), 1: warp-private histograms + match_any (slower on B200) */
 
 /*

@@ -79,6 +79,23 @@ def test_zipf_heavy_hitter(pkg, ctx, oracle):
         assert_plan_equal(g, o, f"zipf/mode{mode}")
 
 
+def test_unnest_hot_list_overflow(pkg, ctx, oracle):
+    """groups longer than one warp expands go to the unnest's hot list; with a list of zero entries the pass is repeated
+    with room for every tuple -- same result."""
+    rng = np.random.default_rng(12)
+    nB, nP = 60000, 3000
+    B = np.zeros((nB, 2), np.uint32); B[:, 0] = np.arange(nB)
+    B[:, 1] = np.where(rng.random(nB) < 0.5, 7, rng.integers(0, 2000, nB)).astype(np.uint32)      # key 7 owns ~30000 rows
+    P = np.zeros((nP, 2), np.uint32); P[:, 0] = rng.integers(0, 2000, nP); P[::5, 0] = 7
+    try:
+        for cap in (0, 16, 1 << 20):
+            ctx.set_option(pkg.capi.OPT_UNNEST_HOT_CAP, cap)
+            g, o = both(pkg, ctx, oracle, 3, B, (8, 4, 4, 0), 1999, P, (8, 0, 4, 0))
+            assert_plan_equal(g, o, f"hot-list cap {cap}")
+    finally:
+        ctx.set_option(pkg.capi.OPT_UNNEST_HOT_CAP, 1 << 20)
+
+
 def test_two_level_fine_partitioning(pkg, ctx, oracle):
     """a directory wide enough that the probe input needs two partition levels to reach shared-memory
     sized fine partitions (> 1024 fine partitions at the test's 4 KiB slices); skewed variant overflows
