@@ -20,7 +20,7 @@ OPT_WARP_AGGREGATE, OPT_PARTITION_BYTES, OPT_PARTITION_WINDOW, OPT_PARTITION_MIN
 OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_SMEM_MIN_PROBE, OPT_SMEM_CHUNK = 5, 6, 7, 8
 OPT_PART_THREADS, OPT_PART_RANK_MATCH, OPT_PROBE_THREADS, OPT_SMEM_BUILD, OPT_SMEM_BUILD_BYTES = 9, 10, 11, 12, 13
 OPT_CLUSTER_PROBE, OPT_CLUSTER_MIN_PROBE, OPT_CLUSTER_MIN_PARTS, OPT_CLUSTER_SLICE_BYTES, OPT_LEAN_PROBE = 14, 15, 16, 17, 18
-OPT_UNNEST_HOT_CAP = 19
+OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
 
 # every symbol include/hj3d.h declares (tests check that the library exports all of them)
 SYMBOLS = [

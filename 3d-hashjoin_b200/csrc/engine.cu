@@ -62,6 +62,8 @@ struct hj3d_ctx {
   int64_t cluster_min_probe = 1ll << 22;    // smaller probe inputs use the other paths
   int64_t cluster_min_parts = 64;           // coarse partitions needed to keep every cluster busy
   int64_t cluster_slice_bytes = 0;          // > 0: cap on the slice's shared memory (tests)
+  int64_t part_sample = 1;                  // regions planned from a sample: 0 never, 1 once this ctx has seen an overflow, 2 always
+  bool    seen_skew = false;
   int64_t unnest_hot_cap = 1ll << 20;       // entries of the unnest's hot-tuple list before it is re-run with room for all
   int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
   int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
@@ -299,6 +301,31 @@ inline uint32_t choose_parts(hj3d_ctx* c, uint64_t table_bytes, uint64_t n_local
   return P;
 }
 
+// Regions sized from a sampled partition histogram (partition.cuh: k_part_sample / k_plan_caps): fills part_start[P + 1]
+// and returns the total capacity.  `tilemap` == nullptr: plain input of n_tiles tiles of `tile` records.
+template <int HASH>
+int plan_regions(hj3d_ctx* c, Src src, bool recs, const uint2* tilemap, uint32_t tile, uint32_t n_tiles, uint32_t stride, Dir d, PartFn pf,
+                 uint32_t P, uint32_t fan, unsigned long long n_total, unsigned long long cap_uniform,
+                 unsigned long long* part_start /* [P + 1] */, unsigned long long* total_out) {
+  unsigned long long *counts_s = nullptr, *caps = nullptr;
+  HJ_TRY(dev_alloc(c, &counts_s, (uint64_t)P + 1));
+  HJ_TRY(dev_alloc(c, &caps, (uint64_t)P + 1));
+  CUDA_TRY(cudaMemsetAsync(counts_s, 0, ((size_t)P + 1) * 8, c->stream));
+  const uint32_t nbs = (n_tiles + stride - 1) / stride;
+  if (nbs) {
+    if (recs) k_part_sample<HASH, true><<<nbs, 256, 0, c->stream>>>(src, tilemap, tile, stride, n_tiles, d, pf, P, fan, counts_s);
+    else      k_part_sample<HASH, false><<<nbs, 256, 0, c->stream>>>(src, tilemap, tile, stride, n_tiles, d, pf, P, fan, counts_s);
+  }
+  k_plan_caps<<<blocks_for((uint64_t)P + 1, 256), 256, 0, c->stream>>>(counts_s, P, n_total, cap_uniform, caps);
+  c->launches += 2;
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{caps}, StoreExU64{part_start}, (uint64_t)P + 1, (DevStats*)nullptr, c->d_scalar + 3)));
+  unsigned long long* h = (unsigned long long*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_scalar + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *total_out = h[0];
+  return HJ3D_OK;
+}
+
 template <int HASH, bool LEFTID>
 int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uint32_t rowid_base,
                     Partitioned<typename HashT<HASH>::key_t>* out) {
@@ -308,30 +335,40 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
   const PartFn pf = make_partfn(width, d.lo);
   const unsigned long long cap = n / P + n / (32ull * P) + 8192;          // expected size + ~3% + constant slack
   out->P = P;
-  HJ_TRY(dev_alloc(c, &out->recs, (uint64_t)P * cap));
-  HJ_TRY(dev_alloc(c, &out->part_start, P));
-  HJ_TRY(dev_alloc(c, &out->counts, P));
-  CUDA_TRY(cudaMemsetAsync(out->counts, 0, (size_t)P * 8, c->stream));
-  k_part_fixed_starts<<<blocks_for(P, 256), 256, 0, c->stream>>>(P, cap, out->part_start);
   const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
   const bool recs = !src.gather && src.stride == sizeof(Slot<KeyT>) && src.key_off == 0 && src.rowid_off == sizeof(KeyT) &&
                     ((uintptr_t)src.base % sizeof(Slot<KeyT>)) == 0 && rowid_base == 0;
   const uint32_t nb = blocks_for(n, kTile);
+  // skewed keys seen before (or forced): plan the regions from a sample instead of assuming equal shares
+  const bool planned = P > 1 && nb > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
+  HJ_TRY(dev_alloc(c, &out->part_start, (uint64_t)P + 1));
+  HJ_TRY(dev_alloc(c, &out->counts, P));
+  unsigned long long total = (unsigned long long)P * cap;
+  if (planned) {
+    const uint32_t stride = nb >= 4096 ? 32u : (nb >= 256 ? 4u : 1u);
+    HJ_TRY((plan_regions<HASH>(c, src, recs, nullptr, (uint32_t)kTile, nb, stride, d, pf, P, P, n, cap, out->part_start, &total)));
+  } else {
+    k_part_fixed_starts<<<blocks_for((uint64_t)P + 1, 256), 256, 0, c->stream>>>(P + 1, cap, out->part_start);
+  }
+  HJ_TRY(dev_alloc(c, &out->recs, total));
+  CUDA_TRY(cudaMemsetAsync(out->counts, 0, (size_t)P * 8, c->stream));
   auto launch = [&](unsigned long long cap_, unsigned long long* cursor_) -> cudaError_t {
     return launch_part_scatter<HASH, LEFTID>(c->stream, recs, (int)c->part_threads, c->part_rank_match != 0, nb, src, nullptr, d, pf,
                                              P, P, rowid_base, cap_, out->part_start, cursor_, out->recs);
   };
-  CUDA_TRY(launch(cap, out->counts));
+  CUDA_TRY(launch(planned ? 0ull : cap, out->counts));
   c->launches += nb ? 2 : 1;
-  unsigned long long* h = (unsigned long long*)c->h_pinned;               // P <= 1024 -> 8 KB
+  unsigned long long* h = (unsigned long long*)c->h_pinned;               // P <= 1024 -> 8 KB counts + 8 KB starts
   CUDA_TRY(cudaMemcpyAsync(h, out->counts, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(h + P, out->part_start, ((size_t)P + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   bool overflow = false; uint64_t kept = 0;
-  for (uint32_t p = 0; p < P; ++p) { kept += h[p]; overflow |= h[p] > cap; }
+  for (uint32_t p = 0; p < P; ++p) { kept += h[p]; overflow |= h[p] > h[P + p + 1] - h[P + p]; }
   out->n_kept = kept;
   if (overflow) {
     // skewed partition sizes: the cursors hold the exact histogram, redo the scatter into exact regions
     out->fallback = true;
+    c->seen_skew = true;
     unsigned long long* counts2 = nullptr;
     HJ_TRY(dev_alloc(c, &counts2, P));
     k_part_prefix<<<1, 32, 0, c->stream>>>(out->counts, P, out->part_start);
@@ -396,26 +433,35 @@ int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
   const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
   const unsigned long long cap2 = n / F + n / (16ull * F) + 2048;
   fine.P = Fall;
-  HJ_TRY(dev_alloc(c, &fine.recs, (uint64_t)Fall * cap2));
-  HJ_TRY(dev_alloc(c, &fine.part_start, Fall));
-  HJ_TRY(dev_alloc(c, &fine.counts, Fall));
-  CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
-  k_fixed_starts_u64<<<blocks_for(Fall, 256), 256, 0, c->stream>>>(Fall, cap2, fine.part_start);
   const PartFn pf = make_partfn(Wf, dir.lo);
   Src rs = records_src(coarse);
+  const bool planned = n_tiles > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
+  HJ_TRY(dev_alloc(c, &fine.part_start, (uint64_t)Fall + 1));
+  HJ_TRY(dev_alloc(c, &fine.counts, Fall));
+  unsigned long long total2 = (unsigned long long)Fall * cap2;
+  if (planned) {
+    const uint32_t stride = n_tiles >= 4096 ? 8u : (n_tiles >= 256 ? 2u : 1u);
+    HJ_TRY((plan_regions<HASH>(c, rs, true, tm, (uint32_t)kTile, n_tiles, stride, dir, pf, Fall, P2, coarse.n_kept, cap2,
+                               fine.part_start, &total2)));
+  } else {
+    k_fixed_starts_u64<<<blocks_for((uint64_t)Fall + 1, 256), 256, 0, c->stream>>>(Fall + 1, cap2, fine.part_start);
+  }
+  HJ_TRY(dev_alloc(c, &fine.recs, total2));
+  CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
   // the ids stored in the coarse records are final (left ids / row ids): level 2 just carries them (LEFTID + RECS)
   CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, dir, pf,
-                                            Fall, P2, 0, cap2, fine.part_start, fine.counts, fine.recs)));
+                                            Fall, P2, 0, planned ? 0ull : cap2, fine.part_start, fine.counts, fine.recs)));
   unsigned long long* d_mx = c->d_scalar;
   CUDA_TRY(cudaMemsetAsync(d_mx, 0, 16, c->stream));
-  k_max_u64<<<64, 256, 0, c->stream>>>(fine.counts, Fall, d_mx);
+  k_part_overflow<<<64, 256, 0, c->stream>>>(fine.counts, fine.part_start, Fall, d_mx);
   c->launches += 3;
   unsigned long long* h = (unsigned long long*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(h, d_mx, 16, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   fine.n_kept = h[1];
-  if (h[0] > cap2) {                             // skew: exact regions from the now known histogram
+  if (h[0]) {                                    // skew: exact regions from the now known histogram
     fine.fallback = true;
+    c->seen_skew = true;
     unsigned long long* counts2 = nullptr;
     HJ_TRY(dev_alloc(c, &counts2, Fall));
     HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{fine.part_start}, Fall, (DevStats*)nullptr, (unsigned long long*)nullptr)));
@@ -1060,7 +1106,7 @@ int hj3d_ctx_create(int device, hj3d_ctx** out) {
   CUDA_TRY(cudaMalloc((void**)&c->d_ctr, sizeof(DevCounters)));
   CUDA_TRY(cudaMalloc((void**)&c->d_stats, kStatsCopies * sizeof(DevStats)));
   CUDA_TRY(cudaMalloc((void**)&c->d_scalar, 4 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMallocHost(&c->h_pinned, 16384));
+  CUDA_TRY(cudaMallocHost(&c->h_pinned, 32768));
   *out = c;
   return HJ3D_OK;
 }
@@ -1108,6 +1154,7 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_CLUSTER_MIN_PROBE: c->cluster_min_probe = v; break;
     case HJ3D_OPT_CLUSTER_MIN_PARTS: if (v >= 1) c->cluster_min_parts = v; break;
     case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
+    case HJ3D_OPT_PART_SAMPLE: if (v >= 0 && v <= 2) c->part_sample = v; break;
     case HJ3D_OPT_UNNEST_HOT_CAP: if (v >= 0 && v <= (1ll << 30)) c->unnest_hot_cap = v; break;
     case HJ3D_OPT_CLUSTER_SLICE_BYTES: c->cluster_slice_bytes = v > 0 ? (v & ~15ll) : 0; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");

@@ -71,6 +71,8 @@ extern "C" {
 #define HJ3D_OPT_CLUSTER_SLICE_BYTES 17 /* cap on the shared memory used for a CTA's table slice (default: all there is) */
 #define HJ3D_OPT_LEAN_PROBE      18 /* 0/1: unique / nested probes of fine partitions use the lean kernel (default 1)  */
 #define HJ3D_OPT_UNNEST_HOT_CAP  19 /* entries of the unnest's hot-tuple list (default 2^20; tests shrink it)           */
+#define HJ3D_OPT_PART_SAMPLE     20 /* partition regions sized from a sampled histogram: 0 never, 1 after this ctx has seen
+                                       an overflow (default), 2 always                                                */
 #define HJ3D_OPT_PART_RANK_MATCH 10 /* 0: rank by shared-memory atomics (default), 1: warp-private histograms + match_any (slower on B200) */
 
 /*

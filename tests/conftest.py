@@ -62,6 +62,7 @@ def ctx(pkg, request):
         c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
         c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096)
         c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
+        c.set_option(pkg.capi.OPT_PART_SAMPLE, 2)            # regions planned from a sampled histogram (what skewed inputs take)
     if request.param == "cluster":
         # thread-block-cluster probe (what 2^30-row probe sides take), forced on at test sizes; tiny slices so
         # that small directories still split into several coarse partitions and some slices overflow
