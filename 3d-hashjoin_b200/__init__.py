@@ -157,6 +157,13 @@ class Table:
                                              int(out_cap), C.byref(c)))
         return rc, c.as_dict()
 
+    def probe_nested_unnest(self, tuples, n, ks, flags=F_CHECKSUM, out=None, out_cap=0):
+        """nested probe directly followed by the unnest, in one kernel: (probe counters, unnest counters)"""
+        pc, uc = Counters(), Counters()
+        rc = capi.check(self.lib.hj3d_probe_nested_unnest(self.ctx.h, self.h, _ptr(tuples), int(n), ks, flags, _ptr(out),
+                                                          int(out_cap), C.byref(pc), C.byref(uc)))
+        return rc, pc.as_dict(), uc.as_dict()
+
     def unnest_pairs(self, nested_pairs, n, flags=F_CHECKSUM, out=None, out_cap=0):
         """deferred unnest of the (left, group ref) pairs exactly as probe_nested wrote them"""
         c = Counters()

@@ -29,7 +29,7 @@ SYMBOLS = [
     "hj3d_ctx_timings",
     "hj3d_table_create", "hj3d_table_build", "hj3d_table_clear", "hj3d_table_destroy", "hj3d_table_stats",
     "hj3d_table_size",
-    "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_group_first_row", "hj3d_gather_u32",
+    "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
     "hj3d_mem_alloc", "hj3d_mem_free", "hj3d_memcpy_h2d", "hj3d_memcpy_d2h", "hj3d_iota_u32",
@@ -108,6 +108,7 @@ def load():
     L.hj3d_probe_nested.argtypes = [vp, vp, vp, u64, KeySpec, vp, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_unnest.argtypes = [vp, vp, vp, vp, u64, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_unnest_pairs.argtypes = [vp, vp, vp, u64, u32, vp, u64, C.POINTER(Counters)]
+    L.hj3d_probe_nested_unnest.argtypes = [vp, vp, vp, u64, KeySpec, u32, vp, u64, C.POINTER(Counters), C.POINTER(Counters)]
     L.hj3d_group_first_row.argtypes = [vp, vp, vp, u64, vp]
     L.hj3d_gather_u32.argtypes = [vp, vp, vp, u64, vp]
     L.hj3d_split_pairs.argtypes = [vp, vp, u64, vp, vp]

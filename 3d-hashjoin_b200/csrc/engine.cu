@@ -18,6 +18,7 @@
 #include "probe_cluster.cuh"
 #include "probe_fine.cuh"
 #include "unnest.cuh"
+#include "probe_unnest.cuh"
 #include "scan.cuh"
 
 using namespace hj3d;
@@ -1015,6 +1016,34 @@ int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2
   return HJ3D_OK;
 }
 
+// nested probe + unnest in one kernel (probe_unnest.cuh).  *fused = false: the input does not take the fine-partition path
+// (small / gathered input); the caller then composes hj3d_probe_nested + hj3d_unnest_pairs.
+template <int HASH>
+int probe_nested_unnest_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* fused) {
+  using KeyT = typename HashT<HASH>::key_t;
+  *fused = false;
+  if (!src.n || src.gather || !c->lean_probe) return HJ3D_OK;
+  ProbePlan<KeyT> pl;
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  if (!pl.smem || !pl.recs || !pl.n_work) return HJ3D_OK;               // (a partition pass that was made is simply not used)
+  PhaseTimer pt(c, PH_PROBE);
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  const size_t sm = pl.fc.smem_bytes;
+  const Slot<KeyT>* recs = (const Slot<KeyT>*)pl.src.base;
+  const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
+#define LAUNCH_PU(C, W) do { \
+    CUDA_TRY(cudaFuncSetAttribute(k_probe_nested_unnest<HASH, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+    k_probe_nested_unnest<HASH, C, W><<<pl.n_work, kFineThreads, sm, c->stream>>>(recs, t->dir, pl.fc, pl.work, pl.work_part, t->goff, groups, \
+                                                                                   t->rows, out, cap, c->d_ctr); } while (0)
+  if (cs) { if (wr) LAUNCH_PU(true, true); else LAUNCH_PU(true, false); }
+  else    { if (wr) LAUNCH_PU(false, true); else LAUNCH_PU(false, false); }
+#undef LAUNCH_PU
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  *fused = true;
+  return HJ3D_OK;
+}
+
 template <class KeyT>
 int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t* gref, const uint2* pairs, uint64_t n, uint32_t flags,
                 uint2* out, uint64_t cap, hj3d_counters* res) {
@@ -1461,6 +1490,55 @@ int hj3d_unnest_pairs(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_nested_pairs
   return out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
 }
 
+int hj3d_probe_nested_unnest(hj3d_ctx* c, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks, uint32_t flags,
+                             uint32_t* d_out, uint64_t cap, hj3d_counters* probe_out, hj3d_counters* unnest_out) {
+  if (!c || !t || !probe_out || !unnest_out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->kind != HJ3D_NESTED) return fail(HJ3D_ERR_INVALID, "hj3d_probe_nested_unnest needs a nested table");
+  if (n && !d_probe) return fail(HJ3D_ERR_INVALID, "d_probe == NULL");
+  if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 probe tuples");
+  HJ_TRY(check_keyspec(ks));
+  HJ_TRY(table_matches(t, ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  memset(probe_out, 0, sizeof(*probe_out)); memset(unnest_out, 0, sizeof(*unnest_out));
+  Src src = make_src(d_probe, n, ks, nullptr);
+  bool fused = false;
+  int rc;
+  switch (ks.hash_id) {
+    case HJ3D_HASH_MURMUR32: rc = probe_nested_unnest_impl<HJ3D_HASH_MURMUR32>(c, t, src, flags, (uint2*)d_out, cap, &fused); break;
+    case HJ3D_HASH_MURMUR64: rc = probe_nested_unnest_impl<HJ3D_HASH_MURMUR64>(c, t, src, flags, (uint2*)d_out, cap, &fused); break;
+    default:                 rc = probe_nested_unnest_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src, flags, (uint2*)d_out, cap, &fused); break;
+  }
+  end_call(c);
+  if (rc < 0) return rc;
+  if (fused) {
+    DevCounters* h = (DevCounters*)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    probe_out->matches = h->matches; probe_out->num_cmps = h->num_cmps; probe_out->out_tuples = h->matches;
+    unnest_out->matches = h->out_cursor; unnest_out->out_tuples = h->out_cursor;
+    unnest_out->checksum_sum = h->checksum_sum; unnest_out->checksum_xor = h->checksum_xor;
+    const bool wr = d_out != nullptr;
+    unnest_out->overflow = (wr && h->out_cursor > cap) ? 1 : 0;
+    unnest_out->out_written = wr ? (h->out_cursor > cap ? cap : h->out_cursor) : 0;
+    return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+  }
+  // composition: nested tuples into a ctx-owned buffer, then the unnest of the pairs
+  auto& hj = c->hj;
+  const size_t need = (n ? n : 1) * 8;
+  if (hj.cnest < need) {
+    if (hj.nest) { cudaStreamSynchronize(c->stream); cudaFree(hj.nest); hj.nest = nullptr; hj.cnest = 0; }
+    HJ_TRY(raw_alloc(&hj.nest, need));
+    hj.cnest = need;
+  }
+  rc = hj3d_probe_nested(c, t, d_probe, n, ks, nullptr, flags & ~HJ3D_F_CHECKSUM, (uint32_t*)hj.nest, n, probe_out);
+  if (rc < 0) return rc;
+  return hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, probe_out->out_written, flags, d_out, cap, unnest_out);
+}
+
 int hj3d_group_first_row(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_gref, uint64_t n, uint32_t* d_out) {
   if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
   if (t->kind != HJ3D_NESTED || !t->built) return fail(HJ3D_ERR_INVALID, "needs a built nested table");
@@ -1534,11 +1612,7 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
     if (rc < 0) return bail(rc);
     n_out = pc->out_written;
   } else {
-    rc = ensure(&hj.nest, &hj.cnest, nP * 8); if (rc < 0) return bail(rc);
-    rc = hj3d_probe_nested(c, t, hj.p, nP, ksP, nullptr, flags, (uint32_t*)hj.nest, nP, pc);
-    if (rc < 0) return bail(rc);
-    const uint64_t m = pc->out_written;
-    rc = hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, m, flags, dOut, cap, uc);
+    rc = hj3d_probe_nested_unnest(c, t, hj.p, nP, ksP, flags, dOut, cap, pc, uc);
     if (rc < 0) return bail(rc);
     n_out = uc->out_written;
   }

@@ -196,6 +196,11 @@ int hj3d_unnest(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_left, const uint
 /* same, reading the (left, group_ref) PAIRS exactly as hj3d_probe_nested wrote them (no column split in between) */
 int hj3d_unnest_pairs(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_nested_pairs, uint64_t n,
                       uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* out);
+/* AlgNestJoinProbe directly followed by AlgUnnestHt (main_experiment1.cc runNrs / runNsr: algebra.hh:435-459 feeding
+ * algebra.hh:510-541): one call, the nested tuples are expanded where they are found and never written.  probe_out gets
+ * the nested probe's count / numCmps, unnest_out the flat result count, checksum and out_written. */
+int hj3d_probe_nested_unnest(hj3d_ctx* ctx, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks, uint32_t flags,
+                             uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* probe_out, hj3d_counters* unnest_out);
 /* first build row id (the MainNode's own tuple) of each group_ref: d_out[i] = data(group d_group_ref[i]) */
 int hj3d_group_first_row(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_group_ref, uint64_t n, uint32_t* d_out);
 /* d_dst[i] = d_src[2*d_idx_pairs_col...]: small column helpers for composing deferred-unnest pipelines */

@@ -118,6 +118,15 @@ def gpu_plan(pkg, ctx, mode, B, ksB, D, P, ksP, gather=None, materialize=True, f
             assert rc2 == rc and cu2 == cu, (cu2, cu)
             assert np.array_equal(sorted_pairs(out2[:cu2["out_written"]].cpu().numpy().view(np.uint32)),
                                   sorted_pairs(out[:cu["out_written"]].cpu().numpy().view(np.uint32)))
+            if gather is None:
+                # nested probe + unnest in one call (fused kernel on the fine-partition path, composition otherwise)
+                out3 = torch.zeros((max(n_out, 1), 2), dtype=torch.int32, device="cuda")
+                rc3, pc3, uc3 = t.probe_nested_unnest(dP, nP, ksP, flags=flags, out=out3, out_cap=n_out)
+                assert rc3 == rc and (pc3["matches"], pc3["num_cmps"]) == (c["matches"], c["num_cmps"]), (pc3, c)
+                assert {k: uc3[k] for k in ("out_tuples", "checksum_sum", "checksum_xor", "out_written")} == \
+                       {k: cu[k] for k in ("out_tuples", "checksum_sum", "checksum_xor", "out_written")}, (uc3, cu)
+                assert np.array_equal(sorted_pairs(out3[:uc3["out_written"]].cpu().numpy().view(np.uint32)),
+                                      sorted_pairs(out[:cu["out_written"]].cpu().numpy().view(np.uint32)))
             res["pairs"] = out[:cu["out_written"]].cpu().numpy().view(np.uint32)
     res["size"] = t.size()
     t.destroy()

@@ -59,11 +59,8 @@ def main():
                 rc, c = table.probe_chaining(P, nP, ksP, unique=(mode == 1), flags=flags, out=out, out_cap=nS if out is not None else 0)
                 tp = ctx.timings(); tu = {"unnest_ms": 0.0}; res = c
             else:
-                rc, c = table.probe_nested(P, nP, ksP, flags=flags, out=nest, out_cap=nP)
-                tp = ctx.timings()
-                m = c["out_written"]
-                rc, res = table.unnest_pairs(nest, m, flags=flags, out=out, out_cap=nS if out is not None else 0)
-                tu = ctx.timings()
+                rc, c, res = table.probe_nested_unnest(P, nP, ksP, flags=flags, out=out, out_cap=nS if out is not None else 0)
+                tp = ctx.timings(); tu = {"unnest_ms": 0.0}
             e1.record(); torch.cuda.synchronize()
             rows.append({"total": e0.elapsed_time(e1), "b_part": tb["partition_ms"], "hist": tb["histogram_ms"], "scan": tb["scan_ms"],
                          "scatter": tb["scatter_ms"], "group": tb["group_ms"], "build": tb["total_ms"],
