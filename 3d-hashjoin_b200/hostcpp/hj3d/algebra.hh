@@ -299,6 +299,11 @@ class AlgUnnestHt : public AlgBase {
     inline void step_device(const hj3d::detail::NestedBatch& b, const ht_nested_t* table, make_nested_t make, globstat_t* g) {
       run_device(table, b.d_left, b.d_gref, b.n, make, g);
     }
+    // AlgNestJoinProbe ran probe + unnest as one device call (hj3d_probe_nested_unnest): only the count arrives here
+    inline void take_fused_count(uint64_t m) {
+      inc(m);
+      if constexpr (hj3d::detail::counts_only<consumer_t>) _consumer->add_count(m);
+    }
     // false: only the number of unnested tuples is needed downstream, nothing has to come back to the host
     inline bool needs_host_tuples() const {
       if constexpr (hj3d::detail::counts_only<consumer_t>) return _consumer->wants_tuples();
@@ -401,6 +406,16 @@ class AlgNestJoinProbe : public AlgBase {
         check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, nullptr, 0, &cnt));
         if constexpr (detail::counts_only<consumer_t>) _consumer->add_count(cnt.matches);
       } else {
+        if constexpr (detail::is_device_unnest<consumer_t>::value) {
+          if (!_consumer->needs_host_tuples()) {                     // probe -> unnest -> count: one fused device call
+            hj3d_counters ucnt{};
+            check(hj3d_probe_nested_unnest(c, table.handle(), dprobe, n, _in.ks, 0, nullptr, 0, &cnt, &ucnt));
+            _consumer->take_fused_count(ucnt.out_tuples);
+            inc(cnt.matches); _numCmps += cnt.num_cmps;
+            _consumer->fin(g); stopTimer();
+            return;
+          }
+        }
         auto* dout = (uint32_t*)_dout.ensure(n * 8 + 8);
         check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, dout, n, &cnt));
         const uint64_t m = cnt.out_written;
