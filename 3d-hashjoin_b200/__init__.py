@@ -80,6 +80,19 @@ class Context:
                                                     _ptr(out), counts))
         return [int(x) for x in counts]
 
+    def probe2_unnest2(self, table_s, table_t, tuples, n, ks, flags=F_CHECKSUM, want_triples=False, out=None, out_cap=0):
+        """exp4's Ndu probe strand as one device pipeline (hj3d_probe2_unnest2): returns (rc, [4 counter dicts], triples, n_out).
+        want_triples: run once count-only to size the result, then materialise (r, s, t) row-id triples in a torch tensor."""
+        cnt = (Counters * 4)()
+        if want_triples and out is None:
+            import torch
+            capi.check(self.lib.hj3d_probe2_unnest2(self.h, table_s.h, table_t.h, _ptr(tuples), int(n), ks, 0, None, 0, cnt))
+            out_cap = int(cnt[3].out_tuples)
+            out = torch.empty((max(out_cap, 1), 3), dtype=torch.int32, device=f"cuda:{self.device}")
+        rc = capi.check(self.lib.hj3d_probe2_unnest2(self.h, table_s.h, table_t.h, _ptr(tuples), int(n), ks, flags, _ptr(out),
+                                                     int(out_cap), cnt))
+        return rc, [c.as_dict() for c in cnt], out, int(cnt[3].out_written)
+
     def join_host(self, mode, h_build, n_build, ks_build, num_buckets, h_probe, n_probe, ks_probe,
                   flags=0, h_out=None, out_cap=0, want_stats=False):
         """hj3d_join_host on host buffers (numpy arrays / pinned torch CPU tensors / raw addresses)."""

@@ -19,7 +19,7 @@ F_DEVICE_RESULT = 2
 OPT_WARP_AGGREGATE, OPT_PARTITION_BYTES, OPT_PARTITION_WINDOW, OPT_PARTITION_MIN_PROBE = 1, 2, 3, 4
 OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_SMEM_MIN_PROBE, OPT_SMEM_CHUNK = 5, 6, 7, 8
 OPT_PART_THREADS, OPT_PART_RANK_MATCH, OPT_PROBE_THREADS, OPT_SMEM_BUILD, OPT_SMEM_BUILD_BYTES = 9, 10, 11, 12, 13
-OPT_CLUSTER_PROBE, OPT_CLUSTER_MIN_PROBE, OPT_CLUSTER_MIN_PARTS, OPT_CLUSTER_SLICE_BYTES, OPT_LEAN_PROBE = 14, 15, 16, 17, 18
+OPT_LEAN_PROBE = 18
 OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
 
 # every symbol include/hj3d.h declares (tests check that the library exports all of them)
@@ -29,7 +29,7 @@ SYMBOLS = [
     "hj3d_ctx_timings",
     "hj3d_table_create", "hj3d_table_build", "hj3d_table_clear", "hj3d_table_destroy", "hj3d_table_stats",
     "hj3d_table_size",
-    "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_group_first_row", "hj3d_gather_u32",
+    "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_probe2_unnest2", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
     "hj3d_mem_alloc", "hj3d_mem_free", "hj3d_memcpy_h2d", "hj3d_memcpy_d2h", "hj3d_iota_u32",
@@ -109,6 +109,7 @@ def load():
     L.hj3d_unnest.argtypes = [vp, vp, vp, vp, u64, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_unnest_pairs.argtypes = [vp, vp, vp, u64, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_probe_nested_unnest.argtypes = [vp, vp, vp, u64, KeySpec, u32, vp, u64, C.POINTER(Counters), C.POINTER(Counters)]
+    L.hj3d_probe2_unnest2.argtypes = [vp, vp, vp, vp, u64, KeySpec, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_group_first_row.argtypes = [vp, vp, vp, u64, vp]
     L.hj3d_gather_u32.argtypes = [vp, vp, vp, u64, vp]
     L.hj3d_split_pairs.argtypes = [vp, vp, u64, vp, vp]

@@ -11,202 +11,27 @@
 
 #include "build.cuh"
 #include "build_nested_fine.cuh"
-#include "common.cuh"
+#include "engine_internal.hh"
 #include "partition.cuh"
 #include "probe.cuh"
 #include "probe_smem.cuh"
-#include "probe_cluster.cuh"
 #include "probe_fine.cuh"
 #include "unnest.cuh"
 #include "probe_unnest.cuh"
 #include "scan.cuh"
 
-using namespace hj3d;
-
-// ------------------------------------------------------------------------------------ errors
-static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-#define CUDA_TRY(expr)                                                                             \
-  do {                                                                                             \
-    cudaError_t _e = (expr);                                                                       \
-    if (_e != cudaSuccess)                                                                         \
-      return fail(HJ3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
-  } while (0)
-
-#define HJ_TRY(expr) do { int _rc = (expr); if (_rc < 0) return _rc; } while (0)
-
-// ------------------------------------------------------------------------------------ objects
-enum Phase { PH_PARTITION, PH_HIST, PH_SCAN, PH_SCATTER, PH_GROUP, PH_PROBE, PH_UNNEST, PH_COUNT };
-
-struct hj3d_ctx {
-  int          device = 0;
-  cudaStream_t stream = nullptr;
-  bool         own_stream = false;
-  cudaMemPool_t pool = nullptr;
-  // options
-  int64_t warp_aggregate = 1;
-  int64_t partition_bytes = 48ll << 20;
-  int64_t partition_window = 8ll << 20;
-  int64_t partition_min_probe = 1ll << 20;
-  int64_t smem_build = 1;                    // build chaining tables range-by-range in shared memory
-  int64_t smem_build_bytes = 64 << 10;       // shared memory budget of one build range
-  int64_t smem_probe = 1;                    // probe through shared-memory resident fine partitions
-  int64_t smem_slice_bytes = 48 << 10;      // shared memory per block for a fine partition's table slice
-  int64_t smem_min_probe = 1ll << 16;       // smaller probe inputs use the global-memory kernels
-  int64_t smem_chunk = 1 << 16;             // probe records per work item
-  int64_t probe_threads = 256;              // shared-memory probe block size (256 | 512)
-  int64_t part_threads = 512;               // partition kernel block size (256 | 512)
-  int64_t part_rank_match = 0;              // rank by warp-private histograms + match_any instead of shared atomics
-  int64_t cluster_probe = 0;                // probe coarse partitions with thread-block clusters (probe_cluster.cuh); experimental:
-                                            // correct on every parity case, not yet faster than the two-level path
-  int64_t cluster_min_probe = 1ll << 22;    // smaller probe inputs use the other paths
-  int64_t cluster_min_parts = 64;           // coarse partitions needed to keep every cluster busy
-  int64_t cluster_slice_bytes = 0;          // > 0: cap on the slice's shared memory (tests)
-  int64_t part_sample = 1;                  // regions planned from a sample: 0 never, 1 once this ctx has seen an overflow, 2 always
-  bool    seen_skew = false;
-  int64_t unnest_hot_cap = 1ll << 20;       // entries of the unnest's hot-tuple list before it is re-run with room for all
-  int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
-  int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
-  // per-phase events of the last call
-  cudaEvent_t ev[PH_COUNT][2];
-  bool        ev_used[PH_COUNT];
-  cudaEvent_t ev_total[2];
-  uint64_t    launches = 0;
-  // small device scratch: counters + stats + scalar, and its pinned host mirror
-  DevCounters* d_ctr = nullptr;
-  DevStats*    d_stats = nullptr;
-  unsigned long long* d_scalar = nullptr;   // 4 scalars
-  void*        h_pinned = nullptr;          // >= 256 B
-  int          sm_count = 148;
-  // grow-only workspace for per-call temporaries: bump allocated, reset at the start of every call, so
-  // steady-state calls (the repeat loop of the drivers) never touch the device allocator
-  struct Chunk { uint8_t* base; size_t cap, used; };
-  std::vector<Chunk> arena;
-  struct HostJoinBufs { void *b = nullptr, *p = nullptr, *out = nullptr, *nest = nullptr, *l = nullptr, *g = nullptr;
-                        size_t cb = 0, cp = 0, cout = 0, cnest = 0, cl = 0, cg = 0; } hj;
-};
-
-struct Buf {  // persistent, grow-only device buffer owned by a table
-  void* p = nullptr; size_t cap = 0;
-};
-
-struct hj3d_table {
-  int      kind = 0;
-  uint64_t D = 0, blo = 0, bhi = 0;        // global bucket count and owned range
-  Dir      dir{};
-  bool     built = false;
-  int      hash_id = -1;
-  uint32_t key_bytes = 0;
-  uint64_t n = 0, n_groups = 0;
-  uint32_t* off = nullptr;                 // [n_local + 1] bucket run starts
-  void*     slots = nullptr;               // Slot<KeyT>[n]     (chaining; temporary for nested)
-  uint32_t* goff = nullptr;                // [n_local + 1]     (nested)
-  void*     groups = nullptr;              // Group<KeyT>[G]    (nested)
-  uint32_t* rows = nullptr;                // [n]               (nested)
-  Buf       b_off, b_slots, b_goff, b_groups, b_rows;   // storage behind the pointers above (kept across clear())
-  uint32_t  parts = 1, part_width = 0;     // bucket-range partitioning used by the build (1 = none)
-  uint32_t  fine_width = 0, fine_parts = 0; // fine partitions whose table slice fits in shared memory
-  DevStats  hstats{};                      // bucket statistics captured during the build
-  bool      have_stats = false;
-};
+std::string& hj3d_err_slot() { static thread_local std::string e; return e; }
 
 namespace {
-
-struct PhaseTimer {
-  hj3d_ctx* c; Phase p;
-  PhaseTimer(hj3d_ctx* c_, Phase p_) : c(c_), p(p_) {
-    if (!c->ev_used[p]) { cudaEventRecord(c->ev[p][0], c->stream); c->ev_used[p] = true; }
-  }
-  ~PhaseTimer() { cudaEventRecord(c->ev[p][1], c->stream); }
-};
-
-inline void begin_call(hj3d_ctx* c) {
-  for (int i = 0; i < PH_COUNT; ++i) c->ev_used[i] = false;
-  cudaEventRecord(c->ev_total[0], c->stream);
-}
-inline void end_call(hj3d_ctx* c) { cudaEventRecord(c->ev_total[1], c->stream); }
-
-int raw_alloc(void** p, size_t bytes) {
-  cudaError_t e = cudaMalloc(p, bytes);
-  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(HJ3D_ERR_NOMEM, "device out of memory"); }
-  if (e != cudaSuccess) return fail(HJ3D_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-  return HJ3D_OK;
-}
-
-// start of a call: all temporaries of the previous call are dead (every call ends with a stream sync or
-// only enqueues work that is ordered before the next call's work on the same stream).  If the previous
-// call had to add chunks, merge them into one so the next call of the same shape bump-allocates only.
-int arena_reset(hj3d_ctx* c) {
-  if (c->arena.size() > 1) {
-    size_t total = 0;
-    for (auto& k : c->arena) total += k.cap;
-    cudaStreamSynchronize(c->stream);
-    for (auto& k : c->arena) cudaFree(k.base);
-    c->arena.clear();
-    void* p = nullptr;
-    HJ_TRY(raw_alloc(&p, total));
-    c->arena.push_back({(uint8_t*)p, total, 0});
-  }
-  for (auto& k : c->arena) k.used = 0;
-  return HJ3D_OK;
-}
-
-template <class T> int dev_alloc(hj3d_ctx* c, T** p, uint64_t count) {
-  *p = nullptr;
-  if (count == 0) count = 1;
-  const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
-  for (auto& k : c->arena)
-    if (k.cap - k.used >= bytes) { *p = (T*)(k.base + k.used); k.used += bytes; return HJ3D_OK; }
-  const size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
-  void* q = nullptr;
-  HJ_TRY(raw_alloc(&q, cap));
-  c->arena.push_back({(uint8_t*)q, cap, bytes});
-  *p = (T*)q;
-  return HJ3D_OK;
-}
-inline void dev_free(hj3d_ctx*, void*) {}   // arena memory is reclaimed wholesale by arena_reset
-
-template <class T> int buf_ensure(hj3d_ctx* c, Buf& b, T** p, uint64_t count) {
-  if (count == 0) count = 1;
-  const size_t bytes = count * sizeof(T);
-  if (b.cap < bytes) {
-    if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
-    HJ_TRY(raw_alloc(&b.p, bytes));
-    b.cap = bytes;
-  }
-  *p = (T*)b.p;
-  return HJ3D_OK;
-}
-inline void buf_release(hj3d_ctx* c, Buf& b) {
-  if (b.p) { if (c) cudaStreamSynchronize(c->stream); cudaFree(b.p); }
-  b.p = nullptr; b.cap = 0;
-}
-
-inline uint32_t blocks_for(uint64_t n, uint32_t per_block) { return (uint32_t)((n + per_block - 1) / per_block); }
-
-inline int check_keyspec(const hj3d_keyspec& ks) {
-  if (ks.hash_id > 2) return fail(HJ3D_ERR_UNSUPPORTED, "unknown hash_id");
-  const uint32_t kb = ks.hash_id == HJ3D_HASH_MURMUR64 ? 8 : 4;
-  if (ks.key_bytes != kb) return fail(HJ3D_ERR_INVALID, "key_bytes does not match hash_id");
-  if (ks.tuple_bytes == 0 || ks.key_offset + kb > ks.tuple_bytes) return fail(HJ3D_ERR_INVALID, "key outside tuple");
-  if (ks.key_offset % kb || ks.tuple_bytes % kb)
-    return fail(HJ3D_ERR_UNSUPPORTED, "key must be naturally aligned inside the row-store tuple");
-  if (ks.rowid_offset != HJ3D_NO_ROWID && (ks.rowid_offset % 4 || ks.rowid_offset + 4 > ks.tuple_bytes))
-    return fail(HJ3D_ERR_INVALID, "rowid_offset outside tuple / misaligned");
-  return HJ3D_OK;
-}
-
-inline Src make_src(const void* d_tuples, uint64_t n, const hj3d_keyspec& ks, const uint32_t* gather) {
-  Src s; s.base = (const uint8_t*)d_tuples; s.gather = gather; s.n = n; s.stride = ks.tuple_bytes;
-  s.key_off = ks.key_offset; s.rowid_off = ks.rowid_offset;
-  return s;
-}
 
 // ---- scan drivers ---------------------------------------------------------------------------------
 template <class T, bool STATS, class Loader, class Storer>
 int run_scan(hj3d_ctx* c, Loader load, Storer store, uint64_t n, DevStats* d_stats, T* d_total) {
   const uint32_t nb = blocks_for(n, kScanTile);
+  if (nb == 0) {                                   // empty input (e.g. a shard that owns no bucket): nothing to scan
+    if (d_total) CUDA_TRY(cudaMemsetAsync(d_total, 0, sizeof(T), c->stream));
+    return HJ3D_OK;
+  }
   T* sums = nullptr;
   HJ_TRY(dev_alloc(c, &sums, nb));
   k_scan_reduce<T, Loader, STATS><<<nb, kScanThreads, 0, c->stream>>>(load, n, sums, d_stats);
@@ -341,14 +166,17 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
                     ((uintptr_t)src.base % sizeof(Slot<KeyT>)) == 0 && rowid_base == 0;
   const uint32_t nb = blocks_for(n, kTile);
   // skewed keys seen before (or forced): plan the regions from a sample instead of assuming equal shares
-  const bool planned = P > 1 && nb > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
+  bool planned = P > 1 && nb > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
   HJ_TRY(dev_alloc(c, &out->part_start, (uint64_t)P + 1));
   HJ_TRY(dev_alloc(c, &out->counts, P));
   unsigned long long total = (unsigned long long)P * cap;
   if (planned) {
     const uint32_t stride = nb >= 4096 ? 32u : (nb >= 256 ? 4u : 1u);
     HJ_TRY((plan_regions<HASH>(c, src, recs, nullptr, (uint32_t)kTile, nb, stride, d, pf, P, P, n, cap, out->part_start, &total)));
-  } else {
+    // tile maps address records with 32 bits: planned regions (each at least the uniform share) can add up to ~2n
+    if (total >= 0xFFFFFFF0ull) { planned = false; total = (unsigned long long)P * cap; }
+  }
+  if (!planned) {
     k_part_fixed_starts<<<blocks_for((uint64_t)P + 1, 256), 256, 0, c->stream>>>(P + 1, cap, out->part_start);
   }
   HJ_TRY(dev_alloc(c, &out->recs, total));
@@ -436,7 +264,7 @@ int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
   fine.P = Fall;
   const PartFn pf = make_partfn(Wf, dir.lo);
   Src rs = records_src(coarse);
-  const bool planned = n_tiles > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
+  bool planned = n_tiles > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
   HJ_TRY(dev_alloc(c, &fine.part_start, (uint64_t)Fall + 1));
   HJ_TRY(dev_alloc(c, &fine.counts, Fall));
   unsigned long long total2 = (unsigned long long)Fall * cap2;
@@ -444,7 +272,9 @@ int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
     const uint32_t stride = n_tiles >= 4096 ? 8u : (n_tiles >= 256 ? 2u : 1u);
     HJ_TRY((plan_regions<HASH>(c, rs, true, tm, (uint32_t)kTile, n_tiles, stride, dir, pf, Fall, P2, coarse.n_kept, cap2,
                                fine.part_start, &total2)));
-  } else {
+    if (total2 >= 0xFFFFFFF0ull) { planned = false; total2 = (unsigned long long)Fall * cap2; }
+  }
+  if (!planned) {
     k_fixed_starts_u64<<<blocks_for((uint64_t)Fall + 1, 256), 256, 0, c->stream>>>(Fall + 1, cap2, fine.part_start);
   }
   HJ_TRY(dev_alloc(c, &fine.recs, total2));
@@ -493,7 +323,7 @@ inline void set_fine_width(hj3d_ctx* c, hj3d_table* t, double payload_bytes_tota
 // build each range in shared memory (k_build_fine).  Returns *done = false when a range does not fit
 // (skewed / heavily duplicated keys): the caller then uses the global-memory kernels below.
 template <int HASH>
-int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT<HASH>::key_t>* slots, bool* done) {
+int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT<HASH>::key_t>* slots, bool* done, uint64_t* kept) {
   using KeyT = typename HashT<HASH>::key_t;
   *done = false;
   const uint64_t n = src.n;
@@ -542,6 +372,7 @@ int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT
   CUDA_TRY(cudaGetLastError());
   if (*h) return HJ3D_OK;                                   // some range overflowed shared memory
   (void)nl;
+  *kept = fine.n_kept;                                      // tuples of buckets outside a shard's range were dropped
   *done = true;
   return HJ3D_OK;
 }
@@ -607,7 +438,7 @@ int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done) {
   Group<KeyT>* groups = nullptr;
   HJ_TRY(buf_ensure(c, t->b_groups, &groups, G));
   if (G) CUDA_TRY(cudaMemcpyAsync(groups, gtmp, G * sizeof(Group<KeyT>), cudaMemcpyDeviceToDevice, c->stream));
-  t->groups = groups; t->n_groups = G; t->n = n; t->slots = nullptr;
+  t->groups = groups; t->n_groups = G; t->n = fine.n_kept; t->slots = nullptr;
   t->parts = 1; t->part_width = nl ? nl : 1;
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -638,9 +469,10 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     set_fine_width(c, t, (double)n * sizeof(Slot<KeyT>));
     HJ_TRY(init_dev_stats_copies(c));
     bool done = false;
-    HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done));
+    uint64_t kept = n;
+    HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done, &kept));
     if (done) {
-      t->n = n; t->parts = 1; t->part_width = nl ? nl : 1;
+      t->n = kept; t->parts = 1; t->part_width = nl ? nl : 1;
       CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
       CUDA_TRY(cudaGetLastError());
       t->have_stats = true; t->built = true;
@@ -657,20 +489,19 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
   const uint2* tilemap = nullptr;
   uint32_t n_tiles = blocks_for(n, kBuildTile);
   Src bsrc = src;
-  uint64_t n_in = n;
+  uint64_t n_kept = n;                                                    // < n only for shard tables fed foreign tuples
   if (P > 1 && n) {
     HJ_TRY((partition_local<HASH, false>(c, src, d, P, width, 0, &pr)));
     uint2* tm = nullptr;
     HJ_TRY(make_tilemap(c, pr, kBuildTile, &tm, &n_tiles));
     tilemap = tm;
     bsrc = records_src(pr);
-    n_in = pr.n_kept;
+    n_kept = pr.n_kept;
     t->parts = P; t->part_width = width;
   } else {
     P = 1;
     t->parts = 1; t->part_width = nl ? nl : 1;
   }
-  (void)n_in;
   DevStats hs; init_dev_stats_host(hs);
   CUDA_TRY(cudaMemcpyAsync(c->d_stats, &hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
   {
@@ -688,8 +519,16 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     const bool want_stats = t->kind == HJ3D_CHAINING;
     if (want_stats) HJ_TRY((run_scan<uint32_t, true>(c, LoadU32{t->off}, StoreInclU32{t->off}, nl, c->d_stats, (uint32_t*)nullptr)));
     else            HJ_TRY((run_scan<uint32_t, false>(c, LoadU32{t->off}, StoreInclU32{t->off}, nl, (DevStats*)nullptr, (uint32_t*)nullptr)));
-    const uint32_t n32 = (uint32_t)n;
-    CUDA_TRY(cudaMemcpyAsync(t->off + nl, &n32, 4, cudaMemcpyHostToDevice, c->stream));
+    // off[nl] = number of tuples kept = inclusive end of the last bucket.  A shard table (its directory is a sub-range
+    // of the buckets) drops tuples of foreign buckets, so the kept count comes from the histogram, not from n.
+    if (nl) CUDA_TRY(cudaMemcpyAsync(t->off + nl, t->off + nl - 1, 4, cudaMemcpyDeviceToDevice, c->stream));
+    else    CUDA_TRY(cudaMemsetAsync(t->off, 0, 4, c->stream));
+    if (nl != t->D && P <= 1) {
+      uint32_t* h = (uint32_t*)c->h_pinned;
+      CUDA_TRY(cudaMemcpyAsync(h, t->off + nl, 4, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      n_kept = *h;
+    }
   }
   {
     PhaseTimer pt(c, PH_SCATTER);
@@ -703,21 +542,22 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
       }
     }
   }
-  t->n = n;
+  t->n = n_kept;
   if (t->kind == HJ3D_NESTED) {
     PhaseTimer pt(c, PH_GROUP);
+    const uint64_t nk = n_kept;                                           // slots [0, nk) are valid
     uint32_t *cell = nullptr, *rep = nullptr, *gcnt = nullptr, *gmin = nullptr, *gidx = nullptr, *gstart = nullptr;
-    HJ_TRY(dev_alloc(c, &cell, n)); HJ_TRY(dev_alloc(c, &rep, n)); HJ_TRY(dev_alloc(c, &gcnt, n));
-    HJ_TRY(dev_alloc(c, &gmin, n)); HJ_TRY(dev_alloc(c, &gidx, n + 1)); HJ_TRY(dev_alloc(c, &gstart, n + 1));
-    CUDA_TRY(cudaMemsetAsync(cell, 0xFF, (n ? n : 1) * 4, c->stream));
-    CUDA_TRY(cudaMemsetAsync(gmin, 0xFF, (n ? n : 1) * 4, c->stream));
-    CUDA_TRY(cudaMemsetAsync(gcnt, 0, (n ? n : 1) * 4, c->stream));
-    if (n) {
-      k_group_claim<HASH><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, n, d, t->off, cell, rep, gcnt, gmin);
+    HJ_TRY(dev_alloc(c, &cell, nk)); HJ_TRY(dev_alloc(c, &rep, nk)); HJ_TRY(dev_alloc(c, &gcnt, nk));
+    HJ_TRY(dev_alloc(c, &gmin, nk)); HJ_TRY(dev_alloc(c, &gidx, nk + 1)); HJ_TRY(dev_alloc(c, &gstart, nk + 1));
+    CUDA_TRY(cudaMemsetAsync(cell, 0xFF, (nk ? nk : 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(gmin, 0xFF, (nk ? nk : 1) * 4, c->stream));
+    CUDA_TRY(cudaMemsetAsync(gcnt, 0, (nk ? nk : 1) * 4, c->stream));
+    if (nk) {
+      k_group_claim<HASH><<<blocks_for(nk, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, nk, d, t->off, cell, rep, gcnt, gmin);
       ++c->launches;
     }
     unsigned long long* d_tot = c->d_scalar;
-    HJ_TRY((run_scan<unsigned long long, false>(c, LoadCells{cell, gcnt, n}, StoreCells{gidx, gstart}, n + 1,
+    HJ_TRY((run_scan<unsigned long long, false>(c, LoadCells{cell, gcnt, nk}, StoreCells{gidx, gstart}, nk + 1,
                                                   (DevStats*)nullptr, d_tot)));
     unsigned long long* h_tot = (unsigned long long*)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -728,27 +568,29 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     HJ_TRY(buf_ensure(c, t->b_groups, &groups, G));
     t->groups = groups;
     HJ_TRY(buf_ensure(c, t->b_goff, &t->goff, (uint64_t)nl + 1));
-    HJ_TRY(buf_ensure(c, t->b_rows, &t->rows, n));
-    if (n) {
-      k_group_emit<HASH><<<blocks_for(n, 256), 256, 0, c->stream>>>(slots, n, cell, gcnt, gmin, gidx, gstart, groups);
+    HJ_TRY(buf_ensure(c, t->b_rows, &t->rows, nk));
+    if (nk) {
+      k_group_emit<HASH><<<blocks_for(nk, 256), 256, 0, c->stream>>>(slots, nk, cell, gcnt, gmin, gidx, gstart, groups);
       ++c->launches;
     }
     k_group_offsets<<<blocks_for((uint64_t)nl + 1, 256), 256, 0, c->stream>>>(t->off, gidx, nl + 1, t->goff);
     ++c->launches;
-    if (n) {   // main chains into first-appearance order (probe.cuh walks them like ht_nested.hh:371-379)
+    if (nk) {   // main chains into first-appearance order (probe.cuh walks them like ht_nested.hh:371-379)
       k_order_groups<KeyT><<<blocks_for(nl, 256), 256, 0, c->stream>>>(t->goff, groups, nl);
       ++c->launches;
     }
-    if (n) {
-      k_group_rows<HASH><<<blocks_for(n, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, n, rep, gstart, t->rows);
+    if (nk) {
+      k_group_rows<HASH><<<blocks_for(nk, kBuildTile), kBuildThreads, 0, c->stream>>>(slots, nk, rep, gstart, t->rows);
       ++c->launches;
     }
     // nested statistics: main chain length per bucket = #distinct keys (ht_nested.hh:459-479)
     uint32_t* dummy = nullptr;
     const uint32_t nb = blocks_for(nl, kScanTile);
     HJ_TRY(dev_alloc(c, &dummy, nb));
-    k_scan_reduce<uint32_t, LoadDiff, true><<<nb, kScanThreads, 0, c->stream>>>(LoadDiff{t->goff}, nl, dummy, c->d_stats);
-    ++c->launches;
+    if (nb) {
+      k_scan_reduce<uint32_t, LoadDiff, true><<<nb, kScanThreads, 0, c->stream>>>(LoadDiff{t->goff}, nl, dummy, c->d_stats);
+      ++c->launches;
+    }
     t->slots = nullptr;                                                   // arena memory, dead after this call
   }
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
@@ -841,86 +683,10 @@ global_path:
   return HJ3D_OK;
 }
 
-// ---- cluster probe (probe_cluster.cuh): one partition pass of fan-out <= 1024, C SMs share a partition's table slice ----
-template <int HASH, int KIND, bool CS, bool WR>
-int launch_probe_cluster(hj3d_ctx* c, hj3d_table* t, const Partitioned<typename HashT<HASH>::key_t>& pr, ClusterCfg cc,
-                         uint2* out, uint64_t cap, bool* ok) {
-  using KeyT = typename HashT<HASH>::key_t;
-  constexpr int C = kClC;
-  auto kfn = k_probe_cluster<HASH, KIND, CS, WR>;
-  const size_t sm = 2 * (size_t)ClTile<KeyT>::kTile * sizeof(Slot<KeyT>) + cc.slice_bytes;
-  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.gridDim = dim3((unsigned)(C * (c->sm_count / C)), 1, 1);
-  cfg.blockDim = dim3(kClThreads, 1, 1);
-  cfg.dynamicSmemBytes = sm;
-  cfg.stream = c->stream;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  int n_clusters = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, kfn, &cfg);
-  if (e != cudaSuccess || n_clusters < 1) { cudaGetLastError(); *ok = false; return HJ3D_OK; }
-  if (getenv("HJ3D_DEBUG")) fprintf(stderr, "[hj3d] cluster probe: C=%d max active clusters=%d parts=%u sub_shift=%u slice_bytes=%u smem=%zu\n",
-                                    C, n_clusters, cc.n_parts, cc.sub_shift, cc.slice_bytes, sm);
-  if ((uint32_t)n_clusters > cc.n_parts) n_clusters = (int)cc.n_parts;
-  cfg.gridDim = dim3((unsigned)(C * n_clusters), 1, 1);
-  const void* rows = KIND == 0 ? (const void*)t->slots : (const void*)t->groups;
-  const uint32_t* off = KIND == 0 ? t->off : t->goff;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kfn, (const Slot<KeyT>*)pr.recs, (const unsigned long long*)pr.part_start,
-                              (const unsigned long long*)pr.counts, t->dir, cc, off, rows, out, (unsigned long long)cap, c->d_ctr));
-  ++c->launches;
-  *ok = true;
-  return HJ3D_OK;
-}
-
-// Geometry: the widest power-of-two bucket range per CTA whose slice fits shared memory, narrowed until the
-// table splits into enough coarse partitions to keep all clusters busy.  *ok = false: use the other paths.
-template <int HASH, int KIND>
-int probe_cluster_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* ok) {
-  using KeyT = typename HashT<HASH>::key_t;
-  using RowT = typename std::conditional<KIND == 0, Slot<KeyT>, Group<KeyT>>::type;
-  constexpr int C = kClC;
-  *ok = false;
-  const uint64_t n = src.n;
-  const uint32_t nl = t->dir.n_local;
-  if (!c->cluster_probe || (int64_t)n < c->cluster_min_probe || nl < 2) return HJ3D_OK;
-  if ((double)n * 1.04 + 8192.0 * kMaxParts >= 4.0e9) return HJ3D_OK;
-  const uint64_t n_rows = KIND == 0 ? t->n : t->n_groups;
-  const size_t staging = 2 * (size_t)ClTile<KeyT>::kTile * sizeof(Slot<KeyT>);
-  int64_t budget = (int64_t)c->smem_optin - 3072 - (int64_t)staging;
-  if (budget < 16384) return HJ3D_OK;
-  if (c->cluster_slice_bytes > 0 && c->cluster_slice_bytes < budget) budget = c->cluster_slice_bytes;
-  const double per_bucket = 2.0 + (double)n_rows * sizeof(RowT) / (double)nl;
-  uint32_t shift = 0;
-  while (shift < 15 && (double)(2u << shift) * per_bucket * 1.04 + 256.0 <= (double)budget) ++shift;   // 2^shift buckets fit
-  while (shift > 0 && ((uint64_t)nl >> (shift + 3)) < (uint64_t)c->cluster_min_parts) --shift;         // enough partitions
-  const uint64_t width = (uint64_t)C << shift;
-  const uint64_t P = ((uint64_t)nl + width - 1) / width;
-  if (P > (uint64_t)kMaxParts || P < (uint64_t)c->cluster_min_parts) return HJ3D_OK;
-  Partitioned<KeyT> pr;
-  HJ_TRY((partition_local<HASH, true>(c, src, t->dir, (uint32_t)P, (uint32_t)width, 0, &pr)));
-  PhaseTimer pt(c, PH_PROBE);
-  ClusterCfg cc{shift, nl, (uint32_t)P, (uint32_t)(budget & ~15ll)};
-  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
-  if (cs) { if (wr) HJ_TRY((launch_probe_cluster<HASH, KIND, true, true>(c, t, pr, cc, out, cap, ok)));
-            else    HJ_TRY((launch_probe_cluster<HASH, KIND, true, false>(c, t, pr, cc, out, cap, ok))); }
-  else    { if (wr) HJ_TRY((launch_probe_cluster<HASH, KIND, false, true>(c, t, pr, cc, out, cap, ok)));
-            else    HJ_TRY((launch_probe_cluster<HASH, KIND, false, false>(c, t, pr, cc, out, cap, ok))); }
-  CUDA_TRY(cudaGetLastError());
-  return HJ3D_OK;
-}
-
 template <int HASH>
 int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
   if (!src.n) return HJ3D_OK;
-  if (!src.gather && unique) {              // at most one result per probe tuple
-    bool ok = false;
-    HJ_TRY((probe_cluster_impl<HASH, 0>(c, t, src, flags, out, cap, &ok)));
-    if (ok) return HJ3D_OK;
-  }
   ProbePlan<KeyT> pl;
   HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
   if (!pl.n_work) return HJ3D_OK;
@@ -970,11 +736,6 @@ template <int HASH>
 int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
   using KeyT = typename HashT<HASH>::key_t;
   if (!src.n) return HJ3D_OK;
-  if (!src.gather) {
-    bool ok = false;
-    HJ_TRY((probe_cluster_impl<HASH, 1>(c, t, src, flags, out, cap, &ok)));
-    if (ok) return HJ3D_OK;
-  }
   ProbePlan<KeyT> pl;
   HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
   if (!pl.n_work) return HJ3D_OK;
@@ -1105,7 +866,7 @@ int table_matches(hj3d_table* t, const hj3d_keyspec& ks) {
 // ------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
-const char* hj3d_last_error(void) { return g_err.c_str(); }
+const char* hj3d_last_error(void) { return hj3d_err_slot().c_str(); }
 const char* hj3d_version(void) { return "hj3d 0.1 (sm_100a)"; }
 uint64_t hj3d_pair_mix(uint32_t l, uint32_t r) { return pair_mix(l, r); }
 
@@ -1179,13 +940,9 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PART_THREADS: if (v == 256 || v == 512 || v == 1024) c->part_threads = v; break;
     case HJ3D_OPT_PART_RANK_MATCH: c->part_rank_match = v != 0; break;
     case HJ3D_OPT_PROBE_THREADS: if (v == 256 || v == 512) c->probe_threads = v; break;
-    case HJ3D_OPT_CLUSTER_PROBE: c->cluster_probe = v != 0; break;
-    case HJ3D_OPT_CLUSTER_MIN_PROBE: c->cluster_min_probe = v; break;
-    case HJ3D_OPT_CLUSTER_MIN_PARTS: if (v >= 1) c->cluster_min_parts = v; break;
     case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
     case HJ3D_OPT_PART_SAMPLE: if (v >= 0 && v <= 2) c->part_sample = v; break;
     case HJ3D_OPT_UNNEST_HOT_CAP: if (v >= 0 && v <= (1ll << 30)) c->unnest_hot_cap = v; break;
-    case HJ3D_OPT_CLUSTER_SLICE_BYTES: c->cluster_slice_bytes = v > 0 ? (v & ~15ll) : 0; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
   }
   return HJ3D_OK;
@@ -1630,17 +1387,6 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
 
 }  // extern "C"
 
-#ifdef HJ3D_CL_TRACE
-extern "C" int hj3d_debug_trace_read(long long* h_rows, unsigned* n) {
-  unsigned cnt = 0;
-  cudaMemcpyFromSymbol(&cnt, hj3d::g_cl_trace_n, sizeof(cnt));
-  cudaMemcpyFromSymbol(h_rows, hj3d::g_cl_trace, sizeof(long long) * hj3d::kTraceRows * hj3d::kTraceCols);
-  unsigned zero = 0;
-  cudaMemcpyToSymbol(hj3d::g_cl_trace_n, &zero, sizeof(zero));
-  *n = cnt < (unsigned)hj3d::kTraceRows ? cnt : (unsigned)hj3d::kTraceRows;
-  return 0;
-}
-#endif
 
 template <int HASH>
 static int partition_by_owner_t(hj3d_ctx* c, Src src, Dir d, uint32_t width, uint32_t n_owners, uint32_t rowid_base,

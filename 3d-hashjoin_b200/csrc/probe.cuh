@@ -258,15 +258,15 @@ __global__ void k_group_first_row(const Group<KeyT>* __restrict__ groups, const 
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = groups[gref[i]].first_row;
 }
-__global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, uint32_t* __restrict__ dst) {
+static __global__ void k_gather_u32(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint64_t n, uint32_t* __restrict__ dst) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[idx[i]];
 }
-__global__ void k_iota_u32(uint32_t* __restrict__ dst, uint64_t n, uint32_t first) {
+static __global__ void k_iota_u32(uint32_t* __restrict__ dst, uint64_t n, uint32_t first) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = first + (uint32_t)i;
 }
-__global__ void k_split_pairs(const uint2* __restrict__ pairs, uint64_t n, uint32_t* __restrict__ l, uint32_t* __restrict__ r) {
+static __global__ void k_split_pairs(const uint2* __restrict__ pairs, uint64_t n, uint32_t* __restrict__ l, uint32_t* __restrict__ r) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const uint2 p = pairs[i]; l[i] = p.x; r[i] = p.y; }
 }

@@ -389,7 +389,9 @@ class AlgNestJoinProbe : public AlgBase {
     using globstat_t = typename consumer_t::globstat_t; using input_t = typename hashfun_t::input_t;
     using output_t = typename consumer_t::input_t; using joinpred_t = Tjoinpred; using concatfun_t = Tconcatfun;
     AlgNestJoinProbe(consumer_t* aConsumer, build_t* aBuildOperator)
-      : AlgBase("AlgNestJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {}
+      : AlgBase("AlgNestJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {
+      hj3d::check_key_equality_predicate<joinpred_t, hashfun_t, typename build_t::hashfun_t>("AlgNestJoinProbe: Tjoinpred");
+    }
     inline void init(globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
     inline void step(input_t* aProbeTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aProbeTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
@@ -477,7 +479,9 @@ class AlgHashJoinProbe : public AlgBase {
     using output_t = typename consumer_t::input_t; using hashvalue_t = typename hashfun_t::output_t;
     using joinpred_t = Tjoinpred; using concatfun_t = Tconcatfun;
     inline AlgHashJoinProbe(consumer_t* aConsumer, build_t* aBuildOperator)
-      : AlgBase("AlgHashJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {}
+      : AlgBase("AlgHashJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {
+      hj3d::check_key_equality_predicate<joinpred_t, hashfun_t, typename build_t::hashfun_t>("AlgHashJoinProbe: Tjoinpred");
+    }
     inline void init([[maybe_unused]] globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
     inline void step(input_t* aTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
@@ -499,11 +503,28 @@ class AlgHashJoinProbe : public AlgBase {
         check(hj3d_probe_chaining(c, table.handle(), dprobe, n, _in.ks, nullptr, IsBuildKeyUnique ? 1 : 0, 0, dout, m, &cnt));
         std::vector<uint32_t> pairs(2 * m);
         check(hj3d_memcpy_d2h(c, pairs.data(), dout, m * 8));
-        // probe order like the tuple-at-a-time reference; the device writes a probe's matches consecutively in
-        // chain-walk order, which a stable sort on the probe position keeps
+        // probe order like the tuple-at-a-time reference; within one probe tuple the reference emits its matches in
+        // chain-walk order = the bucket's oldest tuple first, then newest to second oldest (ht_chaining.hh:185-194).
+        // Matches of one probe are a sub-sequence of that chain, i.e. ordered by build row id: (the chain head if it
+        // matches), then descending.  The device's output order is unspecified, so it is re-established here from
+        // row ids alone; whether the smallest matching row is the chain head is decided by the bucket's minimum row.
         std::vector<uint64_t> order(m);
         for (uint64_t i = 0; i < m; ++i) order[i] = ((uint64_t)pairs[2 * i] << 32) | pairs[2 * i + 1];
-        std::stable_sort(order.begin(), order.end(), [](uint64_t a, uint64_t b) { return (a >> 32) < (b >> 32); });
+        std::sort(order.begin(), order.end(), [](uint64_t a, uint64_t b) {
+          if ((a >> 32) != (b >> 32)) return (a >> 32) < (b >> 32);
+          return (uint32_t)a > (uint32_t)b;                                    // descending build row id
+        });
+        if constexpr (!IsBuildKeyUnique) {
+          const auto head_row = table.bucket_min_rows();                         // bucket -> oldest row id of the bucket
+          for (uint64_t lo = 0; lo < m;) {
+            uint64_t hi = lo + 1;
+            while (hi < m && (order[hi] >> 32) == (order[lo] >> 32)) ++hi;
+            // the last element (smallest row id) moves to the front iff it is the bucket's first inserted tuple
+            const uint32_t smallest = (uint32_t)order[hi - 1];
+            if (hi - lo > 1 && head_row(smallest)) std::rotate(order.begin() + lo, order.begin() + hi - 1, order.begin() + hi);
+            lo = hi;
+          }
+        }
         for (uint64_t i = 0; i < m; ++i) {
           _outputTuple = concatfun_t::eval(_in.seq.at((uint32_t)(order[i] >> 32)), table.row((uint32_t)order[i]));
           _consumer->step(&_outputTuple, g);

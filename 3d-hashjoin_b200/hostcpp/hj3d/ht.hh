@@ -78,11 +78,11 @@ class DeviceTable {
     hashvalue_t hash(const data_t* aData) const { return hashfun_t::eval(aData); }
     size_t      size()                    const { return _rows.size(); }
 
-    void insert(data_t* aData) { _rows.push(aData); _sealed = false; }
-    void insert_bulk(data_t* first, size_t n) { _rows.push_bulk(first, n); _sealed = false; }
+    void insert(data_t* aData) { _rows.push(aData); _sealed = false; _head.clear(); }
+    void insert_bulk(data_t* first, size_t n) { _rows.push_bulk(first, n); _sealed = false; _head.clear(); }
 
     void clear() {                                               // ht_chaining.hh:250-258 / ht_nested.hh:438-447
-      _rows.clear();
+      _rows.clear(); _head.clear();
       check(hj3d_table_clear(Runtime::instance().ctx(), _t));
       _sealed = false;
     }
@@ -109,6 +109,18 @@ class DeviceTable {
     hj3d_table*         handle()  const { const_cast<DeviceTable*>(this)->seal(); return _t; }
     const hj3d_keyspec& keyspec() const { return _ks; }
     data_t*             row(uint32_t rowid) const { return _rows.at(rowid); }
+    // predicate "row id is the first tuple inserted into its bucket" (= the directory entry, the head of the chain walk,
+    // ht_chaining.hh:185-194); only the tuple-materialising host path of AlgHashJoinProbe needs it (emission order)
+    auto bucket_min_rows() const {
+      if (_head.size() != _numBuckets) {
+        _head.assign(_numBuckets, 0xFFFFFFFFu);
+        for (size_t i = 0; i < _rows.size(); ++i) {
+          const size_t b = (size_t)hashfun_t::eval(_rows.at(i)) % _numBuckets;
+          if (_head[b] == 0xFFFFFFFFu) _head[b] = (uint32_t)i;
+        }
+      }
+      return [this](uint32_t rowid) { return _head[(size_t)hashfun_t::eval(_rows.at(rowid)) % _numBuckets] == rowid; };
+    }
 
   protected:
     int          _kind;
@@ -119,6 +131,7 @@ class DeviceTable {
     DevBuf       _dbuild;
     std::vector<std::remove_const_t<data_t>> _staging;
     bool         _sealed = false;
+    mutable std::vector<uint32_t> _head;   // bucket -> first inserted row (lazily, bucket_min_rows)
 };
 
 }  // namespace hj3d::detail
@@ -135,7 +148,9 @@ class HtChaining1 : public hj3d::detail::DeviceTable<Tdata, Thashfun> {
     struct Node { Node* _next; data_t* _data; hashvalue_t _hashvalue; };
 
     HtChaining1(const size_t aNumBuckets, [[maybe_unused]] const uint32_t aReservoirLog2ChunkSize)
-      : base_t(HJ3D_CHAINING, aNumBuckets) {}
+      : base_t(HJ3D_CHAINING, aNumBuckets) {
+      hj3d::check_key_equality_predicate<eqfun_t, hashfun_t, hashfun_t>("HtChaining1: Tcontenteqfun");
+    }
 
     size_t getRsvSize()              const { return this->raw_stats().rsv_main; }          // ht_chaining.hh:113
     size_t memoryConsupmtion()       const { auto s = this->raw_stats(); return s.mem_dir + s.mem_main; }
@@ -169,7 +184,9 @@ class HtNested1 : public hj3d::detail::DeviceTable<Tdata, Thashfun> {
 
     HtNested1(const size_t aNumBuckets, [[maybe_unused]] const uint32_t aMainRsvLog2ChunkSize,
               [[maybe_unused]] const uint32_t aSubRsvLog2ChunkSize)
-      : base_t(HJ3D_NESTED, aNumBuckets) {}
+      : base_t(HJ3D_NESTED, aNumBuckets) {
+      hj3d::check_key_equality_predicate<eqfun_t, hashfun_t, hashfun_t>("HtNested1: Tcontenteqfun");
+    }
 
     size_t getRsvMainSize()              const { return this->raw_stats().rsv_main; }      // ht_nested.hh:192-193
     size_t getRsvSubSize()               const { return this->raw_stats().rsv_sub; }

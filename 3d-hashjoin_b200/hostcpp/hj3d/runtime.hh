@@ -76,7 +76,7 @@ hj3d_keyspec keyspec_of() {
   if constexpr (has_explicit_keyspec<Thashfun>) {
     return Thashfun::hj3d_keyspec();
   } else {
-    using tuple_t = typename Thashfun::input_t;
+    using tuple_t = std::remove_const_t<typename Thashfun::input_t>;
     using out_t = typename Thashfun::output_t;
     static_assert(std::is_trivially_copyable_v<tuple_t>, "hj3d: hash functor input must be a trivially copyable tuple");
     static const hj3d_keyspec cached = [] {
@@ -108,6 +108,48 @@ hj3d_keyspec keyspec_of() {
       return cand[0];
     }();
     return cached;
+  }
+}
+
+// The device compares the raw bits of the key attributes that the two hash functors name (hj3d_keyspec); the
+// reference additionally evaluates a predicate functor per visited node (joinpred_t::eval, algebra.hh:447,647-648;
+// eqfun_t::eval through isMainNodeMatch, ht_nested.hh:241-243).  A predicate that is not equality of those two
+// attributes would silently give different results, so it is checked on random tuple pairs the same way the hash
+// functor is, and rejected otherwise.  Functors over pointer-reaching intermediates (explicit keyspec) cannot be
+// synthesised here; they are checked through their base functors (`hj3d_base`) when they name one.
+template <class Tpred, class HashL, class HashR>
+void check_key_equality_predicate(const char* what) {
+  using left_t = std::remove_const_t<typename Tpred::left_t>;
+  using right_t = std::remove_const_t<typename Tpred::right_t>;
+  if constexpr (has_explicit_keyspec<HashL> || has_explicit_keyspec<HashR>) {
+    return;
+  } else if constexpr (!std::is_same_v<left_t, std::remove_const_t<typename HashL::input_t>> ||
+                       !std::is_same_v<right_t, std::remove_const_t<typename HashR::input_t>> ||
+                       !std::is_trivially_copyable_v<left_t> || !std::is_trivially_copyable_v<right_t>) {
+    return;   // the predicate sees other tuple types than the hash functors (nested intermediates)
+  } else {
+    static const bool ok = [what] {
+      const hj3d_keyspec kl = keyspec_of<HashL>(), kr = keyspec_of<HashR>();
+      if (kl.key_bytes != kr.key_bytes || kl.hash_id != kr.hash_id)
+        throw Error(std::string("hj3d: ") + what + ": probe and build hash functors hash different key types");
+      std::mt19937_64 rng(4242);
+      for (int trial = 0; trial < 64; ++trial) {
+        alignas(left_t) unsigned char lraw[sizeof(left_t)];
+        alignas(right_t) unsigned char rraw[sizeof(right_t)];
+        for (auto& b : lraw) b = (unsigned char)rng();
+        for (auto& b : rraw) b = (unsigned char)rng();
+        const bool equal_keys = (trial & 1) != 0;
+        if (equal_keys) std::memcpy(rraw + kr.key_offset, lraw + kl.key_offset, kl.key_bytes);
+        else if (std::memcmp(rraw + kr.key_offset, lraw + kl.key_offset, kl.key_bytes) == 0) rraw[kr.key_offset] ^= 1;
+        left_t l; right_t r;
+        std::memcpy(&l, lraw, sizeof l); std::memcpy(&r, rraw, sizeof r);
+        if (Tpred::eval(&l, &r) != equal_keys)
+          throw Error(std::string("hj3d: ") + what + " is not equality of the hashed key attributes; the device engine "
+                      "compares exactly the attribute the hash functors name (see INTEGRATION.md)");
+      }
+      return true;
+    }();
+    (void)ok;
   }
 }
 

@@ -65,10 +65,6 @@ extern "C" {
 #define HJ3D_OPT_SMEM_BUILD      12 /* 0/1: build chaining tables range-by-range in shared memory (default 1)    */
 #define HJ3D_OPT_SMEM_BUILD_BYTES 13 /* shared memory budget of one build range (default 64 KiB)               */
 #define HJ3D_OPT_PROBE_THREADS   11 /* shared-memory probe block size: 256 or 512 (default 256)                  */
-#define HJ3D_OPT_CLUSTER_PROBE   14 /* 0/1: probe coarse partitions with thread-block clusters over DSMEM (default 0: experimental) */
-#define HJ3D_OPT_CLUSTER_MIN_PROBE 15 /* probe inputs smaller than this use the other paths (default 2^22)         */
-#define HJ3D_OPT_CLUSTER_MIN_PARTS 16 /* coarse partitions needed before the cluster probe is used (default 64)    */
-#define HJ3D_OPT_CLUSTER_SLICE_BYTES 17 /* cap on the shared memory used for a CTA's table slice (default: all there is) */
 #define HJ3D_OPT_LEAN_PROBE      18 /* 0/1: unique / nested probes of fine partitions use the lean kernel (default 1)  */
 #define HJ3D_OPT_UNNEST_HOT_CAP  19 /* entries of the unnest's hot-tuple list (default 2^20; tests shrink it)           */
 #define HJ3D_OPT_PART_SAMPLE     20 /* partition regions sized from a sampled histogram: 0 never, 1 after this ctx has seen
@@ -201,6 +197,17 @@ int hj3d_unnest_pairs(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_nested_pai
  * the nested probe's count / numCmps, unnest_out the flat result count, checksum and out_written. */
 int hj3d_probe_nested_unnest(hj3d_ctx* ctx, hj3d_table* t, const void* d_probe, uint64_t n, hj3d_keyspec ks, uint32_t flags,
                              uint32_t* d_out_pairs, uint64_t out_cap, hj3d_counters* probe_out, hj3d_counters* unnest_out);
+/* The deferred-unnesting multi-join pipeline of main_experiment4.cc:846-867 (plan Ndu) as one device pipeline:
+ * AlgScan(R) -> AlgNestJoinProbe(table_s) -> AlgNestJoinProbe(table_t, the key reached through r: HashfunNestedRS,
+ * main_experiment4.cc:413-419) -> AlgUnnestHt(table_t) -> AlgUnnestHt(table_s) -> AlgTop.  Both tables are probed with
+ * the probe tuple's own key; only tuples that find a partner in table_s reach table_t (algebra.hh:447-457).  No
+ * intermediate but one (r, S-group, T-group) entry per surviving tuple is materialised.
+ * out4[0] / out4[1] = count and numCmps of the two probes, out4[2] = count of the first unnest (c_unnest_S column of
+ * the driver's CSV: it unpacks T), out4[3] = count of the second unnest = c_top, with the checksum
+ * sum / xor of hj3d_pair_mix((uint32_t)hj3d_pair_mix(r, s), t) over the flat (r, s, t) row-id triples.
+ * d_out_triples (nullable = count / checksum only): uint32 triples (probe row, table_s row, table_t row), order unspecified. */
+int hj3d_probe2_unnest2(hj3d_ctx* ctx, hj3d_table* table_s, hj3d_table* table_t, const void* d_probe, uint64_t n, hj3d_keyspec ks,
+                        uint32_t flags, uint32_t* d_out_triples, uint64_t out_cap, hj3d_counters* out4);
 /* first build row id (the MainNode's own tuple) of each group_ref: d_out[i] = data(group d_group_ref[i]) */
 int hj3d_group_first_row(hj3d_ctx* ctx, hj3d_table* t, const uint32_t* d_group_ref, uint64_t n, uint32_t* d_out);
 /* d_dst[i] = d_src[2*d_idx_pairs_col...]: small column helpers for composing deferred-unnest pipelines */

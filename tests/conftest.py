@@ -35,11 +35,12 @@ def pkg():
     return hj3d_loader.load()
 
 
-@pytest.fixture(scope="session", params=["direct", "partitioned", "smem", "cluster"])
+@pytest.fixture(scope="session", params=["direct", "partitioned", "smem", "default"])
 def ctx(pkg, request):
-    """Every GPU test runs on all four probe paths: in place with global-memory lookups (small inputs),
-    bucket-range partitioned with L2-window lookups, and partitioned into fine partitions probed in
-    shared memory (what large inputs take), the latter two forced on at test sizes."""
+    """Every GPU test runs on four engine configurations: in place with global-memory lookups (small inputs),
+    bucket-range partitioned with L2-window lookups, partitioned into fine partitions probed in shared memory
+    (what large inputs take; the latter two forced on at test sizes), and the DEFAULT options (whatever path the
+    engine picks for the input size, which is what the headline configuration runs)."""
     import torch
     assert torch.cuda.is_available()
     # same stream as torch, so tensor fills / copies and engine kernels are ordered
@@ -63,12 +64,5 @@ def ctx(pkg, request):
         c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096)
         c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
         c.set_option(pkg.capi.OPT_PART_SAMPLE, 2)            # regions planned from a sampled histogram (what skewed inputs take)
-    if request.param == "cluster":
-        # thread-block-cluster probe (what 2^30-row probe sides take), forced on at test sizes; tiny slices so
-        # that small directories still split into several coarse partitions and some slices overflow
-        c.set_option(pkg.capi.OPT_CLUSTER_PROBE, 1)
-        c.set_option(pkg.capi.OPT_CLUSTER_MIN_PROBE, 0)
-        c.set_option(pkg.capi.OPT_CLUSTER_MIN_PARTS, 1)
-        c.set_option(pkg.capi.OPT_CLUSTER_SLICE_BYTES, 8192)
     c.mode = request.param
     return c

@@ -355,3 +355,52 @@ def test_partition_by_owner_and_sharded_join(pkg, ctx, oracle):
         assert merged.as_dict() == o["stats"]
         assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"]
         assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"]))
+
+
+def test_shard_table_built_from_an_unpartitioned_relation(pkg, ctx, oracle):
+    """A shard table skips tuples of foreign buckets (hj3d.h): building every shard straight from the WHOLE relation and
+    probing every shard with the WHOLE probe side must merge to the unsharded result -- the kept count, not n, closes
+    the directory.  G = 8 owners over D = 9 buckets also gives owners an empty range (hj3d_owner_range)."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(41)
+    lib = pkg.capi.load()
+    for (nB, nP, kmax, D, G) in ((30000, 50000, 9000, 1201, 3), (70000, 20000, 300, 9, 8), (400, 900, 50, 5, 4)):
+        B = np.zeros((nB, 2), np.uint32); B[:, 0] = np.arange(nB); B[:, 1] = rng.integers(0, kmax, nB)
+        P = np.zeros((nP, 2), np.uint32); P[:, 0] = rng.integers(0, kmax, nP)
+        dB, dP = to_dev(B), to_dev(P)
+        for mode in (0, 1, 3):
+            o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(8, 4), D, P, pyo.KeySpec(8, 0))
+            parts = (pkg.Stats * G)()
+            tot = {"matches": 0, "num_cmps": 0}
+            pairs = []
+            n_sum = 0
+            for g in range(G):
+                lo, hi = C.c_uint64(), C.c_uint64()
+                lib.hj3d_owner_range(D, G, g, C.byref(lo), C.byref(hi))
+                t = ctx.table(pkg.CHAINING if mode <= 1 else pkg.NESTED, D, shard=(lo.value, hi.value))
+                t.build(dB, nB, KSg(pkg, 8, 4))
+                n_sum += t.size()[0]
+                if mode <= 1:
+                    _, c = t.probe_chaining(dP, nP, KSg(pkg, 8, 0), unique=(mode == 1), flags=0)
+                    out = torch.zeros((max(c["out_tuples"], 1), 2), dtype=torch.int32, device="cuda")
+                    _, c = t.probe_chaining(dP, nP, KSg(pkg, 8, 0), unique=(mode == 1), out=out, out_cap=c["out_tuples"])
+                    pairs.append(out[:c["out_written"]].cpu().numpy().view(np.uint32))
+                else:
+                    nest = torch.zeros((max(nP, 1), 2), dtype=torch.int32, device="cuda")
+                    _, c = t.probe_nested(dP, nP, KSg(pkg, 8, 0), out=nest, out_cap=nP)
+                    m = c["out_written"]
+                    _, u = t.unnest_pairs(nest, m, flags=0)
+                    out = torch.zeros((max(u["out_tuples"], 1), 2), dtype=torch.int32, device="cuda")
+                    _, u = t.unnest_pairs(nest, m, out=out, out_cap=u["out_tuples"])
+                    pairs.append(out[:u["out_written"]].cpu().numpy().view(np.uint32))
+                tot["matches"] += c["matches"]; tot["num_cmps"] += c["num_cmps"]
+                parts[g] = pkg.Stats(**t.stats())
+                t.destroy()
+            assert n_sum == nB, "every build tuple is kept by exactly one shard"
+            merged = pkg.Stats()
+            lib.hj3d_stats_merge(parts, G, C.byref(merged))
+            what = f"shards-from-whole/{(nB, nP, kmax, D, G)}/mode{mode}"
+            assert merged.as_dict() == o["stats"], what
+            assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"], what
+            assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"])), what
