@@ -14,7 +14,7 @@ from .capi import (CHAINING, F_CHECKSUM, HASH_MURMUR32, HASH_MURMUR64, HASH_MURM
                    OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_WARP_AGGREGATE, Counters, Hj3dError, KeySpec,
                    Stats, Timings)
 
-__all__ = ["Context", "Table", "KeySpec", "Hj3dError", "CHAINING", "NESTED", "F_CHECKSUM", "capi"]
+__all__ = ["Context", "Table", "Comm", "Parts", "KeySpec", "Hj3dError", "CHAINING", "NESTED", "F_CHECKSUM", "capi"]
 
 
 def _ptr(t):
@@ -111,6 +111,88 @@ class Context:
         return rc, pc.as_dict(), uc.as_dict(), (st.as_dict() if want_stats else None)
 
 
+class Parts:
+    """hj3d_parts: this rank's bucket ranges of a relation after the exchange (coarse-partitioned (key, global row id) records)."""
+
+    def __init__(self, lib, h):
+        self.lib, self.h = lib, h
+
+    def info(self):
+        n, sent, lo, hi, ov = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_int()
+        capi.check(self.lib.hj3d_parts_info(self.h, C.byref(n), C.byref(sent), C.byref(lo), C.byref(hi), C.byref(ov)))
+        return {"n_records": int(n.value), "n_sent_remote": int(sent.value), "bucket_lo": int(lo.value), "bucket_hi": int(hi.value),
+                "overflow": int(ov.value)}
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.lib.hj3d_parts_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Comm:
+    """hj3d_comm: one rank of the multi-GPU exchange (include/hj3d.h, csrc/exchange.cu)."""
+
+    def __init__(self, ctx, h, world, rank):
+        self.ctx, self.lib, self.h, self.world, self.rank = ctx, ctx.lib, h, world, rank
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        capi.check(capi.load().hj3d_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, ctx, world, rank, id128=None):
+        h = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(id128) if id128 is not None else None
+        capi.check(ctx.lib.hj3d_comm_create(ctx.h, world, rank, buf, C.byref(h)))
+        return cls(ctx, h, world, rank)
+
+    @classmethod
+    def local(cls, ctxs):
+        """all ranks in this process (one context per rank; contexts may share a device)"""
+        n = len(ctxs)
+        arr = (C.c_void_p * n)(*[c.h for c in ctxs])
+        out = (C.c_void_p * n)()
+        capi.check(ctxs[0].lib.hj3d_comm_create_local(arr, n, out))
+        return [cls(ctxs[r], C.c_void_p(out[r]), n, r) for r in range(n)]
+
+    def set_option(self, opt, v):
+        capi.check(self.lib.hj3d_comm_set_option(self.h, opt, int(v)))
+
+    def reserve(self, slot, records, key_bytes=4):
+        capi.check(self.lib.hj3d_comm_reserve(self.h, slot, int(records), key_bytes))
+
+    def shard(self, num_buckets):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        capi.check(self.lib.hj3d_comm_shard(self.h, int(num_buckets), C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def begin(self, slot, tuples, n, ks, num_buckets, rowid_base, flags=0):
+        capi.check(self.lib.hj3d_exchange_begin(self.h, slot, _ptr(tuples), int(n), ks, int(num_buckets), int(rowid_base), flags))
+
+    def end(self, slot, tuples, rowid_base, rowid_bound=0):
+        """returns (rc, Parts); rc == OVERFLOW: a receive region overflowed somewhere (retry with XCHG_EXACT / more room)"""
+        h = C.c_void_p()
+        rc = capi.check(self.lib.hj3d_exchange_end(self.h, slot, _ptr(tuples), int(rowid_base), int(rowid_bound), C.byref(h)))
+        return rc, Parts(self.lib, h)
+
+    def exchange(self, slot, tuples, n, ks, num_buckets, rowid_base, rowid_bound=0, flags=0):
+        self.begin(slot, tuples, n, ks, num_buckets, rowid_base, flags)
+        return self.end(slot, tuples, rowid_base, rowid_bound)
+
+    def destroy(self):
+        if getattr(self, "h", None):
+            self.lib.hj3d_comm_destroy(self.h)
+        self.h = None
+
+
 class Table:
     """hj3d_table: the chaining (HtChaining1) or nested (HtNested1) table of one build operator."""
 
@@ -142,6 +224,10 @@ class Table:
     def clear(self):
         capi.check(self.lib.hj3d_table_clear(self.ctx.h, self.h))
 
+    def set_rowid_bound(self, bound):
+        capi.check(self.lib.hj3d_table_set_rowid_bound(self.ctx.h, self.h, int(bound)))
+        return self
+
     def stats(self):
         s = Stats()
         capi.check(self.lib.hj3d_table_stats(self.ctx.h, self.h, C.byref(s)))
@@ -151,6 +237,16 @@ class Table:
         n, g = C.c_uint64(), C.c_uint64()
         capi.check(self.lib.hj3d_table_size(self.h, C.byref(n), C.byref(g)))
         return int(n.value), int(g.value)
+
+    def build_parts(self, parts):
+        capi.check(self.lib.hj3d_table_build_parts(self.ctx.h, self.h, parts.h))
+        return self
+
+    def probe_parts(self, parts, mode, flags=F_CHECKSUM, out=None, out_cap=0):
+        """probe with an exchanged relation: mode 0 / 1 chaining (1 = IsBuildKeyUnique), 2 nested, 3 nested + unnest"""
+        pc, uc = Counters(), Counters()
+        rc = capi.check(self.lib.hj3d_probe_parts(self.ctx.h, self.h, parts.h, mode, flags, _ptr(out), int(out_cap), C.byref(pc), C.byref(uc)))
+        return rc, pc.as_dict(), uc.as_dict()
 
     def probe_chaining(self, tuples, n, ks, unique=False, gather=None, flags=F_CHECKSUM, out=None, out_cap=0):
         c = Counters()

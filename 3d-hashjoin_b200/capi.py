@@ -21,6 +21,9 @@ OPT_SMEM_PROBE, OPT_SMEM_SLICE_BYTES, OPT_SMEM_MIN_PROBE, OPT_SMEM_CHUNK = 5, 6,
 OPT_PART_THREADS, OPT_PART_RANK_MATCH, OPT_PROBE_THREADS, OPT_SMEM_BUILD, OPT_SMEM_BUILD_BYTES = 9, 10, 11, 12, 13
 OPT_LEAN_PROBE = 18
 OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
+OPT_PACKED_PROBE, OPT_PACKED_MIN_PROBE, OPT_PACKED_SLICE_BYTES = 21, 22, 23
+XCHG_EXACT = 1
+XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH = 1, 2
 
 # every symbol include/hj3d.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -28,9 +31,12 @@ SYMBOLS = [
     "hj3d_ctx_create", "hj3d_ctx_destroy", "hj3d_ctx_set_stream", "hj3d_ctx_set_option", "hj3d_ctx_sync",
     "hj3d_ctx_timings",
     "hj3d_table_create", "hj3d_table_build", "hj3d_table_clear", "hj3d_table_destroy", "hj3d_table_stats",
-    "hj3d_table_size",
+    "hj3d_table_size", "hj3d_table_set_rowid_bound",
     "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_probe2_unnest2", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
+    "hj3d_comm_unique_id", "hj3d_comm_create", "hj3d_comm_create_local", "hj3d_comm_set_option", "hj3d_comm_destroy",
+    "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
+    "hj3d_table_build_parts", "hj3d_probe_parts",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
     "hj3d_mem_alloc", "hj3d_mem_free", "hj3d_memcpy_h2d", "hj3d_memcpy_d2h", "hj3d_iota_u32",
 ]
@@ -103,6 +109,7 @@ def load():
     L.hj3d_table_clear.argtypes = [vp, vp]
     L.hj3d_table_destroy.argtypes = [vp, vp]
     L.hj3d_table_stats.argtypes = [vp, vp, C.POINTER(Stats)]
+    L.hj3d_table_set_rowid_bound.argtypes = [vp, vp, u64]
     L.hj3d_table_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_probe_chaining.argtypes = [vp, vp, vp, u64, KeySpec, vp, i32, u32, vp, u64, C.POINTER(Counters)]
     L.hj3d_probe_nested.argtypes = [vp, vp, vp, u64, KeySpec, vp, u32, vp, u64, C.POINTER(Counters)]
@@ -115,6 +122,19 @@ def load():
     L.hj3d_split_pairs.argtypes = [vp, vp, u64, vp, vp]
     L.hj3d_join_host.argtypes = [vp, i32, vp, u64, KeySpec, u64, vp, u64, KeySpec, u32, vp, u64,
                                  C.POINTER(Counters), C.POINTER(Counters), C.POINTER(Stats)]
+    L.hj3d_comm_unique_id.argtypes = [vp]
+    L.hj3d_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.hj3d_comm_create_local.argtypes = [C.POINTER(vp), i32, C.POINTER(vp)]
+    L.hj3d_comm_set_option.argtypes = [vp, i32, C.c_int64]
+    L.hj3d_comm_destroy.argtypes = [vp]
+    L.hj3d_comm_reserve.argtypes = [vp, i32, u64, u32]
+    L.hj3d_comm_shard.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
+    L.hj3d_exchange_begin.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32]
+    L.hj3d_exchange_end.argtypes = [vp, i32, vp, u32, u64, C.POINTER(vp)]
+    L.hj3d_parts_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
+    L.hj3d_parts_destroy.argtypes = [vp]
+    L.hj3d_table_build_parts.argtypes = [vp, vp, vp]
+    L.hj3d_probe_parts.argtypes = [vp, vp, vp, i32, u32, vp, u64, C.POINTER(Counters), C.POINTER(Counters)]
     L.hj3d_partition_by_owner.argtypes = [vp, vp, u64, KeySpec, u64, u32, u32, vp, C.POINTER(u64)]
     L.hj3d_owner_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_stats_merge.argtypes = [C.POINTER(Stats), u32, C.POINTER(Stats)]

@@ -16,6 +16,7 @@
 #include "probe.cuh"
 #include "probe_smem.cuh"
 #include "probe_fine.cuh"
+#include "probe_packed.cuh"   // PackCfg + launch_probe_packed (kernels are instantiated in probe_packed.cu)
 #include "unnest.cuh"
 #include "probe_unnest.cuh"
 #include "scan.cuh"
@@ -98,7 +99,7 @@ int init_dev_stats_copies(hj3d_ctx* c) {
 // clear(): the table becomes empty but keeps its device buffers for the next build of the repeat loop
 void clear_table(hj3d_table* t) {
   t->off = nullptr; t->slots = nullptr; t->goff = nullptr; t->groups = nullptr; t->rows = nullptr;
-  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false; t->parts = 1; t->part_width = 0; t->fine_width = 0; t->fine_parts = 0;
+  t->built = false; t->n = 0; t->n_groups = 0; t->have_stats = false; t->pk_ok = false; t->parts = 1; t->part_width = 0; t->fine_width = 0; t->fine_parts = 0;
 }
 void free_table_arrays(hj3d_ctx* c, hj3d_table* t) {
   clear_table(t);
@@ -158,8 +159,8 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
   using KeyT = typename HashT<HASH>::key_t;
   PhaseTimer pt(c, PH_PARTITION);
   const uint64_t n = src.n;
-  const PartFn pf = make_partfn(width, d.lo);
-  const unsigned long long cap = n / P + n / (32ull * P) + 8192;          // expected size + ~3% + constant slack
+  const PartFn pf = make_partfn(width, d.lo, d.n_local);
+  const unsigned long long cap = (n / P + n / (32ull * P) + 8192) & ~1ull; // expected size + ~3% + constant slack; even: 16-byte aligned regions
   out->P = P;
   const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
   const bool recs = !src.gather && src.stride == sizeof(Slot<KeyT>) && src.key_off == 0 && src.rowid_off == sizeof(KeyT) &&
@@ -233,36 +234,71 @@ template <class KeyT> Src records_src(const Partitioned<KeyT>& pr) {
   return s;
 }
 
+// gather the segments of a pre-partitioned relation into one contiguous record array (general paths need a plain input)
+template <class KeyT>
+__global__ void k_compact_segments(const Slot<KeyT>* __restrict__ recs, const unsigned long long* __restrict__ seg_start,
+                                   const unsigned long long* __restrict__ seg_count, const unsigned long long* __restrict__ dst_start,
+                                   Slot<KeyT>* __restrict__ out) {
+  const unsigned long long n = seg_count[blockIdx.x], s0 = seg_start[blockIdx.x], d0 = dst_start[blockIdx.x];
+  for (unsigned long long i = (unsigned long long)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.y * blockDim.x)
+    out[d0 + i] = recs[s0 + i];
+}
+template <class KeyT>
+int make_contiguous(hj3d_ctx* c, Src* src, const PartsView* pre) {
+  Slot<KeyT>* out = nullptr; unsigned long long* dst = nullptr;
+  HJ_TRY(dev_alloc(c, &out, src->n));
+  HJ_TRY(dev_alloc(c, &dst, (uint64_t)pre->n_seg + 1));
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{pre->seg_count}, StoreExU64{dst}, pre->n_seg, (DevStats*)nullptr, (unsigned long long*)nullptr)));
+  if (pre->n_seg && src->n) {
+    k_compact_segments<KeyT><<<dim3(pre->n_seg, 16), 256, 0, c->stream>>>((const Slot<KeyT>*)src->base, pre->seg_start, pre->seg_count, dst, out);
+    ++c->launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  src->base = (const uint8_t*)out;
+  return HJ3D_OK;
+}
+
 // Partition `src` into the F fine bucket ranges of width Wf (one level if F <= 1024, else coarse
 // partitions of P2 consecutive fine ones first).  *ok = false: not representable (caller falls back).
 template <int HASH, bool LEFTID>
 int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
-                   Partitioned<typename HashT<HASH>::key_t>* fine_out, bool* ok) {
+                   Partitioned<typename HashT<HASH>::key_t>* fine_out, bool* ok, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   Partitioned<KeyT>& fine = *fine_out;
   const uint64_t n = src.n;
   const uint32_t nl = dir.n_local;
   *ok = true;
-  if (F <= (uint32_t)kMaxParts) {
+  if (!pre && F <= (uint32_t)kMaxParts) {
     HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, F, Wf, 0, &fine)));
     return HJ3D_OK;
   }
   // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
   uint32_t P2 = 32;
-  while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
-  const uint64_t wc = (uint64_t)Wf * P2;
-  const uint32_t P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
-  if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { *ok = false; return HJ3D_OK; }
+  uint64_t wc;
   Partitioned<KeyT> coarse;
-  HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, P1, (uint32_t)wc, 0, &coarse)));
+  uint32_t P1;
+  if (pre) {   // level 1 happened elsewhere (the exchange): the coarse ranges are given, as segments
+    wc = pre->range_width;
+    if (wc == 0 || wc % Wf != 0 || wc / Wf > (uint64_t)kMaxParts) { *ok = false; return HJ3D_OK; }
+    P2 = (uint32_t)(wc / Wf);
+    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+    coarse.recs = (Slot<KeyT>*)src.base; coarse.part_start = const_cast<unsigned long long*>(pre->seg_start);
+    coarse.counts = const_cast<unsigned long long*>(pre->seg_count); coarse.P = pre->n_seg; coarse.n_kept = n;
+  } else {
+    while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
+    wc = (uint64_t)Wf * P2;
+    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+    if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { *ok = false; return HJ3D_OK; }
+    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, P1, (uint32_t)wc, 0, &coarse)));
+  }
   uint2* tm = nullptr; uint32_t n_tiles = 0;
   const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
   HJ_TRY(make_tilemap(c, coarse, kTile, &tm, &n_tiles));
   PhaseTimer pt(c, PH_PARTITION);
   const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
-  const unsigned long long cap2 = n / F + n / (16ull * F) + 2048;
+  const unsigned long long cap2 = (n / F + n / (16ull * F) + 2048) & ~1ull;
   fine.P = Fall;
-  const PartFn pf = make_partfn(Wf, dir.lo);
+  const PartFn pf = make_partfn(Wf, dir.lo, dir.n_local);
   Src rs = records_src(coarse);
   bool planned = n_tiles > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
   HJ_TRY(dev_alloc(c, &fine.part_start, (uint64_t)Fall + 1));
@@ -318,12 +354,35 @@ inline void set_fine_width(hj3d_ctx* c, hj3d_table* t, double payload_bytes_tota
   t->fine_parts = nl ? (nl + fw - 1) / fw : 1;
 }
 
+// compressed slices (probe_packed.cuh): 2 B of run start + one 32-bit (quotient | row id) word per row
+inline void set_packed_geometry(hj3d_ctx* c, hj3d_table* t) {
+  t->pk_ok = false;
+  const uint32_t nl = t->dir.n_local;
+  if (t->kind != HJ3D_CHAINING || t->hash_id != HJ3D_HASH_MURMUR32 || !t->rowid_bound || !nl || !t->n) return;
+  uint32_t qbits = 0, rbits = 0;
+  for (uint64_t q = 0xFFFFFFFFull / t->D; q; q >>= 1) ++qbits;             // quotient = hash / D
+  for (uint64_t r = t->rowid_bound - 1; r; r >>= 1) ++rbits;
+  if (rbits == 0) rbits = 1;
+  if (qbits + rbits > 32) return;
+  const double per_bucket = 2.0 + 4.0 * (double)t->n / (double)nl;
+  const double w = 0.985 * ((double)c->packed_slice_bytes - 64.0) / per_bucket;   // a slice that overflows falls back to global lookups
+  if (w < 2.0) return;
+  uint32_t fw = w >= (double)nl ? nl : (uint32_t)w;
+  if (fw < nl) { uint32_t p2 = 1; while (p2 * 2 <= fw) p2 *= 2; fw = p2; }
+  if ((double)fw * (double)t->n / (double)nl * 1.02 + 64.0 > 65535.0) {      // 16-bit run starts
+    while (fw > 1 && (double)fw * (double)t->n / (double)nl * 1.02 + 64.0 > 65535.0) fw >>= 1;
+  }
+  t->pk_width = fw; t->pk_parts = (nl + fw - 1) / fw; t->pk_rowid_bits = 32 - qbits;
+  t->pk_ok = true;
+}
+
 // ---- build ----------------------------------------------------------------------------------------
 // Chaining tables over large inputs: partition the build side into fine bucket ranges and let one block
 // build each range in shared memory (k_build_fine).  Returns *done = false when a range does not fit
 // (skewed / heavily duplicated keys): the caller then uses the global-memory kernels below.
 template <int HASH>
-int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT<HASH>::key_t>* slots, bool* done, uint64_t* kept) {
+int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT<HASH>::key_t>* slots, bool* done, uint64_t* kept,
+                        const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   *done = false;
   const uint64_t n = src.n;
@@ -344,7 +403,7 @@ int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT
   if ((double)n * 1.08 + 4096.0 * (double)F >= 4.0e9) return HJ3D_OK;
   Partitioned<KeyT> fine;
   bool ok = false;
-  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok)));
+  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok, pre)));
   if (!ok) return HJ3D_OK;
   PhaseTimer pt(c, PH_SCATTER);
   unsigned long long* base = nullptr;
@@ -380,7 +439,7 @@ int build_chaining_fine(hj3d_ctx* c, hj3d_table* t, Src src, Slot<typename HashT
 // Nested tables over large inputs: the same fine bucket ranges, grouped by key in shared memory
 // (build_nested_fine.cuh).  *done = false: a range or a bucket is too large (skew) -> global-memory kernels.
 template <int HASH>
-int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done) {
+int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   *done = false;
   const uint64_t n = src.n;
@@ -400,7 +459,7 @@ int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done) {
   if ((double)n * 1.08 + 4096.0 * (double)F >= 4.0e9) return HJ3D_OK;
   Partitioned<KeyT> fine;
   bool ok = false;
-  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok)));
+  HJ_TRY((partition_fine<HASH, false>(c, src, t->dir, Wf, F, &fine, &ok, pre)));
   if (!ok) return HJ3D_OK;
   PhaseTimer pt(c, PH_GROUP);
   unsigned long long* base = nullptr;
@@ -449,17 +508,27 @@ int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done) {
 }
 
 template <int HASH>
-int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
+int build_impl(hj3d_ctx* c, hj3d_table* t, Src src, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   const uint64_t n = src.n;
   const uint32_t nl = t->dir.n_local;
   const Dir d = t->dir;
   const bool agg = c->warp_aggregate != 0;
   Slot<KeyT>* slots = nullptr;
+  if (nl == 0) {   // a shard that owns no bucket (hj3d_owner_range with fewer buckets than owners): every tuple is foreign
+    HJ_TRY(buf_ensure(c, t->b_off, &t->off, 1));
+    CUDA_TRY(cudaMemsetAsync(t->off, 0, 4, c->stream));
+    if (t->kind == HJ3D_NESTED) { HJ_TRY(buf_ensure(c, t->b_goff, &t->goff, 1)); CUDA_TRY(cudaMemsetAsync(t->goff, 0, 4, c->stream)); }
+    t->n = 0; t->n_groups = 0; t->parts = 1; t->part_width = 1; t->fine_width = 0; t->fine_parts = 1;
+    init_dev_stats_host(t->hstats);
+    t->have_stats = true; t->built = true;
+    return HJ3D_OK;
+  }
   if (t->kind == HJ3D_NESTED) {
     bool done = false;
-    HJ_TRY(build_nested_fine<HASH>(c, t, src, &done));
+    HJ_TRY(build_nested_fine<HASH>(c, t, src, &done, pre));
     if (done) return HJ3D_OK;
+    if (pre) { HJ_TRY(make_contiguous<KeyT>(c, &src, pre)); pre = nullptr; }
   }
   HJ_TRY(buf_ensure(c, t->b_off, &t->off, (uint64_t)nl + 1));
   if (t->kind == HJ3D_CHAINING) HJ_TRY(buf_ensure(c, t->b_slots, &slots, n));
@@ -470,7 +539,7 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
     HJ_TRY(init_dev_stats_copies(c));
     bool done = false;
     uint64_t kept = n;
-    HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done, &kept));
+    HJ_TRY(build_chaining_fine<HASH>(c, t, src, slots, &done, &kept, pre));
     if (done) {
       t->n = kept; t->parts = 1; t->part_width = nl ? nl : 1;
       CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
@@ -478,6 +547,7 @@ int build_impl(hj3d_ctx* c, hj3d_table* t, Src src) {
       t->have_stats = true; t->built = true;
       return HJ3D_OK;
     }
+    if (pre) { HJ_TRY(make_contiguous<KeyT>(c, &src, pre)); pre = nullptr; }
   }
 
   // bucket-order the input first when the directory + slots do not fit the L2 window budget
@@ -629,8 +699,14 @@ template <class KeyT> struct ProbePlan {
 };
 
 template <int HASH>
-int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HASH>::key_t>* pl) {
+int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HASH>::key_t>* pl, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
+  if (pre) {   // pre-partitioned input: only the fine-partition path continues from the given coarse ranges
+    const bool fine_path = c->smem_probe && t->fine_width && (int64_t)src.n >= c->smem_min_probe && t->fine_parts > 1 &&
+                           (double)src.n * 1.08 + 4096.0 * (double)t->fine_parts < 4.0e9 &&
+                           pre->range_width % t->fine_width == 0 && pre->range_width / t->fine_width <= (uint32_t)kMaxParts;
+    if (!fine_path) { HJ_TRY(make_contiguous<KeyT>(c, &src, pre)); pre = nullptr; }
+  }
   pl->src = src;
   pl->recs = !src.gather && src.stride == sizeof(Slot<KeyT>) && src.key_off == 0 && src.rowid_off == sizeof(KeyT) &&
              ((uintptr_t)src.base % sizeof(Slot<KeyT>)) == 0;
@@ -659,7 +735,7 @@ int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HAS
     }
     Partitioned<KeyT> fine;
     bool ok = false;
-    HJ_TRY((partition_fine<HASH, true>(c, src, t->dir, Wf, F, &fine, &ok)));
+    HJ_TRY((partition_fine<HASH, true>(c, src, t->dir, Wf, F, &fine, &ok, pre)));
     if (!ok) { pl->smem = false; goto global_path; }
     HJ_TRY(make_tilemap(c, fine, chunk, &work, &pl->n_work, &wpart));
     pl->work = work; pl->work_part = wpart;
@@ -683,12 +759,47 @@ global_path:
   return HJ3D_OK;
 }
 
+// Unique chaining probes of large inputs over compressed slices (probe_packed.cuh).  *done = false: not applicable
+// (the caller continues with the general paths).
+inline int probe_packed_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* done, const PartsView* pre) {
+  constexpr int HASH = HJ3D_HASH_MURMUR32;
+  *done = false;
+  const uint32_t F = t->pk_parts, Wf = t->pk_width, nl = t->dir.n_local;
+  if (F < 2 || (double)src.n * 1.08 + 4096.0 * (double)F >= 4.0e9) return HJ3D_OK;
+  Partitioned<uint32_t> fine;
+  bool ok = false;
+  HJ_TRY((partition_fine<HASH, true>(c, src, t->dir, Wf, F, &fine, &ok, pre)));
+  if (!ok) return HJ3D_OK;
+  uint2* work = nullptr; uint32_t* wpart = nullptr; uint32_t n_work = 0;
+  HJ_TRY(make_tilemap(c, fine, 1u << 18, &work, &n_work, &wpart));
+  if (!n_work) { *done = true; return HJ3D_OK; }
+  PhaseTimer pt(c, PH_PROBE);
+  PackCfg pc{};
+  pc.width = Wf; pc.n_local = nl; pc.smem_bytes = (uint32_t)c->packed_slice_bytes; pc.rowid_bits = t->pk_rowid_bits;
+  pc.pow2 = t->dir.is_pow2; pc.qshift = 0;
+  while (pc.pow2 && (1ull << pc.qshift) < t->D) ++pc.qshift;
+  pc.qmagic = t->dir.magic;
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  const size_t sm = pc.smem_bytes;
+  CUDA_TRY(launch_probe_packed(c->stream, cs, wr, n_work, sm, (const Slot<uint32_t>*)fine.recs, t->dir, pc, work, wpart, t->off,
+                               (const Slot<uint32_t>*)t->slots, out, cap, c->d_ctr));
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  *done = true;
+  return HJ3D_OK;
+}
+
 template <int HASH>
-int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap) {
+int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32_t flags, uint2* out, uint64_t cap, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
-  if (!src.n) return HJ3D_OK;
+  if (!src.n || !t->dir.n_local) return HJ3D_OK;
+  if (HASH == HJ3D_HASH_MURMUR32 && unique && !src.gather && c->packed_probe && t->pk_ok && (int64_t)src.n >= c->packed_min_probe) {
+    bool done = false;
+    HJ_TRY(probe_packed_impl(c, t, src, flags, out, cap, &done, pre));
+    if (done) return HJ3D_OK;
+  }
   ProbePlan<KeyT> pl;
-  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl, pre));
   if (!pl.n_work) return HJ3D_OK;
   PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
@@ -733,11 +844,11 @@ int probe_chaining_impl(hj3d_ctx* c, hj3d_table* t, Src src, bool unique, uint32
 }
 
 template <int HASH>
-int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap) {
+int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
-  if (!src.n) return HJ3D_OK;
+  if (!src.n || !t->dir.n_local) return HJ3D_OK;
   ProbePlan<KeyT> pl;
-  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl, pre));
   if (!pl.n_work) return HJ3D_OK;
   PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
@@ -780,12 +891,13 @@ int probe_nested_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2
 // nested probe + unnest in one kernel (probe_unnest.cuh).  *fused = false: the input does not take the fine-partition path
 // (small / gathered input); the caller then composes hj3d_probe_nested + hj3d_unnest_pairs.
 template <int HASH>
-int probe_nested_unnest_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* fused) {
+int probe_nested_unnest_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags, uint2* out, uint64_t cap, bool* fused,
+                             const PartsView* pre = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   *fused = false;
-  if (!src.n || src.gather || !c->lean_probe) return HJ3D_OK;
+  if (!src.n || src.gather || !c->lean_probe || !t->dir.n_local) return HJ3D_OK;
   ProbePlan<KeyT> pl;
-  HJ_TRY(plan_probe<HASH>(c, t, src, &pl));
+  HJ_TRY(plan_probe<HASH>(c, t, src, &pl, pre));
   if (!pl.smem || !pl.recs || !pl.n_work) return HJ3D_OK;               // (a partition pass that was made is simply not used)
   PhaseTimer pt(c, PH_PROBE);
   const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
@@ -941,6 +1053,9 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PART_RANK_MATCH: c->part_rank_match = v != 0; break;
     case HJ3D_OPT_PROBE_THREADS: if (v == 256 || v == 512) c->probe_threads = v; break;
     case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
+    case HJ3D_OPT_PACKED_PROBE: c->packed_probe = v != 0; break;
+    case HJ3D_OPT_PACKED_MIN_PROBE: c->packed_min_probe = v; break;
+    case HJ3D_OPT_PACKED_SLICE_BYTES: if (v >= 1024 && v <= (110 << 10)) c->packed_slice_bytes = v & ~15ll; break;
     case HJ3D_OPT_PART_SAMPLE: if (v >= 0 && v <= 2) c->part_sample = v; break;
     case HJ3D_OPT_UNNEST_HOT_CAP: if (v >= 0 && v <= (1ll << 30)) c->unnest_hot_cap = v; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown option");
@@ -1052,6 +1167,16 @@ int hj3d_table_build(hj3d_ctx* c, hj3d_table* t, const void* d_tuples, uint64_t 
   }
   end_call(c);
   if (rc < 0) { clear_table(t); return rc; }
+  // row ids are positions unless the tuples carry their own (then only the caller can bound them)
+  t->rowid_bound = ks.rowid_offset == HJ3D_NO_ROWID ? (n ? n : 1) : t->rowid_bound_user;
+  set_packed_geometry(c, t);
+  return HJ3D_OK;
+}
+
+int hj3d_table_set_rowid_bound(hj3d_ctx* c, hj3d_table* t, uint64_t bound) {
+  if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  t->rowid_bound_user = bound;
+  if (t->built && t->hash_id >= 0) { /* takes effect at the next build */ }
   return HJ3D_OK;
 }
 
@@ -1296,6 +1421,105 @@ int hj3d_probe_nested_unnest(hj3d_ctx* c, hj3d_table* t, const void* d_probe, ui
   return hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, probe_out->out_written, flags, d_out, cap, unnest_out);
 }
 
+// ---- build / probe continuing from an exchanged (coarse-partitioned) relation: exchange.cu ---------------------------
+static Src parts_src(const hj3d_parts* p) {
+  Src s; s.base = (const uint8_t*)p->recs; s.gather = nullptr; s.n = p->n_total; s.stride = p->key_bytes == 8 ? 16 : 8;
+  s.key_off = 0; s.rowid_off = p->key_bytes;
+  return s;
+}
+static hj3d_keyspec parts_ks(const hj3d_parts* p) {
+  hj3d_keyspec ks; ks.tuple_bytes = p->key_bytes == 8 ? 16 : 8; ks.key_offset = 0; ks.key_bytes = p->key_bytes; ks.hash_id = p->hash_id;
+  ks.rowid_offset = p->key_bytes;
+  return ks;
+}
+static int parts_fit_table(const hj3d_parts* p, const hj3d_table* t) {
+  if (p->overflow) return fail(HJ3D_ERR_INVALID, "the exchange overflowed a receive region: reserve more and exchange again");
+  if (p->D != t->D || p->bucket_lo != t->blo || p->bucket_hi != t->bhi)
+    return fail(HJ3D_ERR_INVALID, "the exchanged relation was partitioned for another directory / bucket range than the table's (hj3d_comm_shard)");
+  return HJ3D_OK;
+}
+
+int hj3d_table_build_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p) {
+  if (!c || !t || !p) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (t->built) return fail(HJ3D_ERR_INVALID, "table is not empty: call hj3d_table_clear first (bulk build)");
+  HJ_TRY(parts_fit_table(p, t));
+  CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
+  begin_call(c);
+  const PartsView pv{p->d_start, p->d_count, p->n_ranges * p->n_src, p->range_width};
+  const Src src = parts_src(p);
+  t->hash_id = (int)p->hash_id; t->key_bytes = p->key_bytes;
+  int rc;
+  switch (p->hash_id) {
+    case HJ3D_HASH_MURMUR32: rc = build_impl<HJ3D_HASH_MURMUR32>(c, t, src, &pv); break;
+    case HJ3D_HASH_MURMUR64: rc = build_impl<HJ3D_HASH_MURMUR64>(c, t, src, &pv); break;
+    default:                 rc = build_impl<HJ3D_HASH_MURMUR64_SEXT32>(c, t, src, &pv); break;
+  }
+  end_call(c);
+  if (rc < 0) { clear_table(t); return rc; }
+  t->rowid_bound = p->rowid_bound ? p->rowid_bound : t->rowid_bound_user;   // global row ids: bounded by the global relation size
+  set_packed_geometry(c, t);
+  return HJ3D_OK;
+}
+
+int hj3d_probe_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32_t flags, uint32_t* d_out, uint64_t cap,
+                     hj3d_counters* probe_out, hj3d_counters* unnest_out) {
+  if (!c || !t || !p || !probe_out) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (mode < 0 || mode > 3) return fail(HJ3D_ERR_INVALID, "mode must be 0..3");
+  if (mode == 3 && !unnest_out) return fail(HJ3D_ERR_INVALID, "unnest_out == NULL");
+  if ((mode <= 1) != (t->kind == HJ3D_CHAINING)) return fail(HJ3D_ERR_INVALID, "probe mode does not match the table kind");
+  HJ_TRY(parts_fit_table(p, t));
+  const hj3d_keyspec ks = parts_ks(p);
+  HJ_TRY(table_matches(t, ks));
+  CUDA_TRY(cudaSetDevice(c->device));
+  HJ_TRY(arena_reset(c));
+  begin_call(c);
+  CUDA_TRY(cudaMemsetAsync(c->d_ctr, 0, sizeof(DevCounters), c->stream));
+  memset(probe_out, 0, sizeof(*probe_out));
+  if (unnest_out) memset(unnest_out, 0, sizeof(*unnest_out));
+  const PartsView pv{p->d_start, p->d_count, p->n_ranges * p->n_src, p->range_width};
+  const Src src = parts_src(p);
+  bool fused = false;
+  int rc;
+#define HJ_BY_HASH(CALL) switch (p->hash_id) { case HJ3D_HASH_MURMUR32: { constexpr int H = HJ3D_HASH_MURMUR32; rc = CALL; } break; \
+                                              case HJ3D_HASH_MURMUR64: { constexpr int H = HJ3D_HASH_MURMUR64; rc = CALL; } break; \
+                                              default: { constexpr int H = HJ3D_HASH_MURMUR64_SEXT32; rc = CALL; } break; }
+  if (mode <= 1)      { HJ_BY_HASH((probe_chaining_impl<H>(c, t, src, mode == 1, flags, (uint2*)d_out, cap, &pv))); }
+  else if (mode == 2) { HJ_BY_HASH((probe_nested_impl<H>(c, t, src, flags, (uint2*)d_out, cap, &pv))); }
+  else                { HJ_BY_HASH((probe_nested_unnest_impl<H>(c, t, src, flags, (uint2*)d_out, cap, &fused, &pv))); }
+#undef HJ_BY_HASH
+  end_call(c);
+  if (rc < 0) return rc;
+  if (mode <= 2) {
+    HJ_TRY(fetch_counters(c, probe_out, cap, d_out != nullptr));
+    return probe_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+  }
+  if (fused) {
+    DevCounters* h = (DevCounters*)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    probe_out->matches = h->matches; probe_out->num_cmps = h->num_cmps; probe_out->out_tuples = h->matches;
+    unnest_out->matches = h->out_cursor; unnest_out->out_tuples = h->out_cursor;
+    unnest_out->checksum_sum = h->checksum_sum; unnest_out->checksum_xor = h->checksum_xor;
+    const bool wr = d_out != nullptr;
+    unnest_out->overflow = (wr && h->out_cursor > cap) ? 1 : 0;
+    unnest_out->out_written = wr ? (h->out_cursor > cap ? cap : h->out_cursor) : 0;
+    return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+  }
+  // not the fine-partition path (small shard): nested tuples into a ctx-owned buffer, then the unnest of the pairs
+  auto& hj = c->hj;
+  const size_t need = (p->n_total ? p->n_total : 1) * 8;
+  if (hj.cnest < need) {
+    if (hj.nest) { cudaStreamSynchronize(c->stream); cudaFree(hj.nest); hj.nest = nullptr; hj.cnest = 0; }
+    HJ_TRY(raw_alloc(&hj.nest, need));
+    hj.cnest = need;
+  }
+  rc = hj3d_probe_parts(c, t, p, 2, flags & ~HJ3D_F_CHECKSUM, (uint32_t*)hj.nest, p->n_total, probe_out, nullptr);
+  if (rc < 0) return rc;
+  return hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, probe_out->out_written, flags, d_out, cap, unnest_out);
+}
+
 int hj3d_group_first_row(hj3d_ctx* c, hj3d_table* t, const uint32_t* d_gref, uint64_t n, uint32_t* d_out) {
   if (!c || !t) return fail(HJ3D_ERR_INVALID, "NULL argument");
   if (t->kind != HJ3D_NESTED || !t->built) return fail(HJ3D_ERR_INVALID, "needs a built nested table");
@@ -1393,7 +1617,7 @@ static int partition_by_owner_t(hj3d_ctx* c, Src src, Dir d, uint32_t width, uin
                                 void* d_out, uint64_t* h_counts) {
   using KeyT = typename HashT<HASH>::key_t;
   PhaseTimer pt(c, PH_PARTITION);
-  const PartFn pf = make_partfn(width, 0);
+  const PartFn pf = make_partfn(width, 0, d.D);
   unsigned long long *counts = nullptr, *starts = nullptr, *cursor = nullptr;
   HJ_TRY(dev_alloc(c, &counts, n_owners)); HJ_TRY(dev_alloc(c, &starts, n_owners)); HJ_TRY(dev_alloc(c, &cursor, n_owners));
   CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)n_owners * 8, c->stream));

@@ -50,6 +50,11 @@ struct hj3d_ctx {
   int64_t part_sample = 1;                  // regions planned from a sample: 0 never, 1 once this ctx has seen an overflow, 2 always
   bool    seen_skew = false;
   int64_t unnest_hot_cap = 1ll << 20;       // entries of the unnest's hot-tuple list before it is re-run with room for all
+  int64_t packed_probe = 0;                 // unique chaining probes over compressed slices (probe_packed.cuh) when the table allows it.
+                                            // Off by default: measured at 2^27 x 2^30 it needs 8x fewer fine partitions but its probe
+                                            // kernel is issue bound at 7.0 ms against 5.4 ms for k_probe_fine
+  int64_t packed_min_probe = 1ll << 22;     // smaller probe inputs use the other paths
+  int64_t packed_slice_bytes = 100 << 10;   // shared memory of one k_probe_packed block: two blocks (+ static + reserved) per SM's 228 KB
   int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
   int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // per-phase events of the last call
@@ -91,8 +96,35 @@ struct hj3d_table {
   Buf       b_off, b_slots, b_goff, b_groups, b_rows;   // storage behind the pointers above (kept across clear())
   uint32_t  parts = 1, part_width = 0;     // bucket-range partitioning used by the build (1 = none)
   uint32_t  fine_width = 0, fine_parts = 0; // fine partitions whose table slice fits in shared memory
+  uint64_t  rowid_bound = 0;               // row ids stored in the table are < rowid_bound (0 = unknown)
+  uint64_t  rowid_bound_user = 0;          // the caller's promise for tuples that carry their own row id (hj3d_table_set_rowid_bound)
+  bool      pk_ok = false;                 // compressed-slice geometry (probe_packed.cuh) usable
+  uint32_t  pk_width = 0, pk_parts = 0, pk_rowid_bits = 0;
   DevStats  hstats{};                      // bucket statistics captured during the build
   bool      have_stats = false;
+};
+
+// A relation that is already bucket-range partitioned at the coarse level (what the multi-GPU exchange delivers,
+// exchange.cu): records of range p live in n_src segments recs[seg_start[q] .. +seg_count[q]), q = p * n_src + source.
+struct PartsView {
+  const unsigned long long* seg_start;   // device [n_seg]
+  const unsigned long long* seg_count;   // device [n_seg]
+  uint32_t n_seg;
+  uint32_t range_width;                  // buckets per coarse range (ranges are aligned to the shard's first bucket)
+};
+
+struct hj3d_parts {
+  void*    recs = nullptr;               // this rank's receive buffer: Slot<KeyT> records (owned by the comm)
+  uint32_t key_bytes = 4, hash_id = 0;
+  uint64_t D = 0, bucket_lo = 0, bucket_hi = 0;
+  uint32_t n_ranges = 0, n_src = 1, range_width = 0;
+  uint64_t cap_seg = 0;
+  unsigned long long* d_start = nullptr; // device [n_ranges * n_src]
+  unsigned long long* d_count = nullptr; // device [n_ranges * n_src]
+  uint64_t n_total = 0;                  // records received
+  uint64_t n_sent_remote = 0;            // records this rank wrote into other GPUs' buffers
+  uint64_t rowid_bound = 0;              // global relation size (row ids are global positions)
+  int      overflow = 0;                 // a segment exceeded its capacity
 };
 
 struct PhaseTimer {

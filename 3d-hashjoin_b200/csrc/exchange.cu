@@ -1,0 +1,495 @@
+// exchange.cu -- the multi-GPU data plane: bucket-range sharding of a relation over the GPUs of one node.
+//
+// The join shards by bucket range: equal keys -> equal bucket, so a partition that is a function of the bucket index keeps
+// every chain / key group on one GPU.  The exchange IS partition level 1 of the engine: a rank partitions its slice of a
+// relation into the coarse bucket ranges the local join works with anyway, and the partition kernel stores every range
+// straight into the receive buffer of the GPU that owns it -- peer-mapped memory, so the sorted runs of a tile travel
+// over NVLink as the kernel writes them (k_part_scatter<.., PEER>, partition.cuh).  There is no separate all-to-all and
+// no host round trip between partitioning and the local join: what a rank receives is already the coarse-partitioned
+// input of its build / probe pipeline (hj3d_table_build_parts / hj3d_probe_parts continue at partition level 2).
+//
+// Receive buffer of a rank: one region of cap_seg records per (owned range, source rank); a source reserves space in
+// "its" regions with its own cursors, so no remote atomics are needed.  The per-(source, range) counts travel by ONE
+// small all-gather, which is also the barrier that orders every peer's stores before the owner's reads.
+//   * one process per GPU  : NCCL for the count all-gather, CUDA IPC to map the peers' receive buffers
+//   * one process, N GPUs  : a local group (hj3d_comm_create_local): plain peer access, events and copies
+// Skewed keys (Zipf) overflow fixed-capacity regions; HJ3D_XCHG_EXACT first exchanges a histogram and then packs the
+// regions tightly at exact offsets (two passes over the local slice).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <memory>
+
+#include "engine_internal.hh"
+#include "partition.cuh"
+
+namespace {
+
+// ---- NCCL, loaded at run time (the library is only needed for multi-process sharding) -------------------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (h) return true;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) { err = "libnccl lacks a required symbol"; h = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi& nccl() { static NcclApi a; return a; }
+
+#define NCCL_TRY(expr)                                                                                       \
+  do {                                                                                                       \
+    ncclResult_t _r = (expr);                                                                                \
+    if (_r != ncclSuccess) return fail(HJ3D_ERR_CUDA, std::string(#expr) + ": " + nccl().GetErrorString(_r)); \
+  } while (0)
+
+constexpr int kSlots = 2;              // relations in flight (build side, probe side)
+constexpr uint32_t kMaxRanges = 1024;
+
+struct ExchangePlan {
+  uint64_t D = 0;
+  uint32_t width = 0, n_ranges = 0, rpo = 1, rpo_shift = 0;   // bucket ranges, ranges per owner (power of two)
+  uint64_t lo(uint32_t r) const { const uint64_t v = (uint64_t)r * rpo * width; return v < D ? v : D; }
+  uint64_t hi(uint32_t r) const { const uint64_t v = (uint64_t)(r + 1) * rpo * width; return v < D ? v : D; }
+  uint32_t owned(uint32_t r) const { const uint64_t a = (uint64_t)r * rpo, b = a + rpo; return a >= n_ranges ? 0u : (uint32_t)((b < n_ranges ? b : n_ranges) - a); }
+};
+
+struct LocalGroup;   // single-process mode: what the ranks share
+
+}  // namespace
+
+struct hj3d_comm {
+  hj3d_ctx* ctx = nullptr;
+  int world = 1, rank = 0;
+  ncclComm_t nc = nullptr;                       // multi-process mode
+  std::shared_ptr<LocalGroup> group;             // single-process mode
+  int64_t target_ranges = 256, min_width = 16384;
+  // receive buffers of this rank and the peers' mapped views of them
+  void*    recv[kSlots] = {nullptr, nullptr};
+  uint64_t recv_records[kSlots] = {0, 0};
+  uint32_t rec_bytes[kSlots] = {8, 8};
+  void*    peer_recv[kSlots][kMaxPeers] = {};
+  bool     peer_is_ipc[kSlots][kMaxPeers] = {};
+  // per-slot exchange state
+  unsigned long long* d_cursor[kSlots] = {nullptr, nullptr};   // [kMaxRanges] my counts per range
+  unsigned long long* d_all[kSlots] = {nullptr, nullptr};      // [world][kMaxRanges] everybody's counts
+  unsigned long long* d_pstart[kSlots] = {nullptr, nullptr};   // [kMaxRanges + 1] my region offsets inside the owners' buffers
+  cudaEvent_t ev_scatter[kSlots] = {nullptr, nullptr};
+  ExchangePlan plan[kSlots];
+  uint64_t cap_seg[kSlots] = {0, 0};
+  hj3d_keyspec ks[kSlots] = {};
+  uint64_t n_local[kSlots] = {0, 0};
+  bool exact[kSlots] = {false, false};
+  bool pending[kSlots] = {false, false};
+  void* h_pinned = nullptr;                      // world * kMaxRanges * 8 bytes
+};
+
+namespace {
+
+struct LocalGroup { std::vector<hj3d_comm*> ranks; };
+
+ExchangePlan make_plan(const hj3d_comm* cm, uint64_t D) {
+  ExchangePlan p; p.D = D;
+  uint64_t w = 1;
+  const uint64_t want = (D + (uint64_t)cm->target_ranges - 1) / (uint64_t)cm->target_ranges;
+  while (w < want) w <<= 1;
+  uint64_t mw = 1; while ((int64_t)mw < cm->min_width) mw <<= 1;
+  if (w < mw) w = mw;
+  while ((D + w - 1) / w > kMaxRanges) w <<= 1;
+  p.width = (uint32_t)(w > 0x80000000ull ? 0x80000000ull : w);
+  p.n_ranges = (uint32_t)((D + p.width - 1) / p.width);
+  uint32_t per = (p.n_ranges + cm->world - 1) / cm->world;
+  p.rpo = 1; p.rpo_shift = 0;
+  while (p.rpo < per) { p.rpo <<= 1; ++p.rpo_shift; }
+  return p;
+}
+
+// region offsets (uniform mode): range q of owner o = q >> shift, segment of source `me`
+__global__ void k_xchg_starts(uint32_t n_ranges, uint32_t rpo_shift, uint32_t world, uint32_t me, unsigned long long cap_seg,
+                              unsigned long long* __restrict__ pstart) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > n_ranges) return;
+  const uint32_t local = q & ((1u << rpo_shift) - 1u);
+  pstart[q] = ((unsigned long long)local * world + me) * cap_seg;
+}
+
+// owner side: segment table of my ranges from the gathered counts.  uniform: fixed regions; exact: tightly packed
+__global__ void k_xchg_segments(const unsigned long long* __restrict__ all, uint32_t stride, uint32_t world, uint32_t first_range,
+                                uint32_t n_owned, unsigned long long cap_seg, int exact,
+                                unsigned long long* __restrict__ seg_start, unsigned long long* __restrict__ seg_count) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  unsigned long long run = 0;
+  for (uint32_t p = 0; p < n_owned; ++p)
+    for (uint32_t s = 0; s < world; ++s) {
+      const unsigned long long cnt = all[(size_t)s * stride + first_range + p];
+      const uint32_t q = p * world + s;
+      seg_start[q] = exact ? run : (unsigned long long)q * cap_seg;
+      seg_count[q] = (!exact && cnt > cap_seg) ? cap_seg : cnt;      // what was actually stored (overflow is reported on the host)
+      run += cnt;
+    }
+}
+
+template <int HASH>
+int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap) {
+  using KeyT = typename HashT<HASH>::key_t;
+  hj3d_ctx* c = cm->ctx;
+  const ExchangePlan& pl = cm->plan[slot];
+  constexpr int TH = 512;
+  const int kTile = TH * PartCfg<KeyT>::kItems;
+  const uint32_t nb = blocks_for(src.n, kTile);
+  if (!nb) return HJ3D_OK;
+  PeerOut peer{};
+  for (int r = 0; r < cm->world; ++r) peer.base[r] = cm->peer_recv[slot][r];
+  peer.owner_shift = pl.rpo_shift;
+  const Dir d = make_dir(pl.D, 0, pl.D);
+  const PartFn pf = make_partfn(pl.width, 0, (uint32_t)pl.D);
+  const size_t sm = part_smem_bytes<KeyT>(pl.n_ranges, TH, false);
+  auto kfn = k_part_scatter<HASH, false, false, TH, false, true>;
+  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  kfn<<<nb, TH, sm, c->stream>>>(src, nullptr, d, pf, pl.n_ranges, pl.n_ranges, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot],
+                                 (Slot<KeyT>*)nullptr, peer);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+template <int HASH>
+int launch_hist(hj3d_comm* cm, int slot, Src src) {
+  hj3d_ctx* c = cm->ctx;
+  const ExchangePlan& pl = cm->plan[slot];
+  const uint32_t nb = blocks_for(src.n, kPartTile);
+  if (!nb) return HJ3D_OK;
+  k_part_hist<HASH><<<nb, kPartThreads, 0, c->stream>>>(src, make_dir(pl.D, 0, pl.D), make_partfn(pl.width, 0, (uint32_t)pl.D), pl.n_ranges, cm->d_cursor[slot]);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  return HJ3D_OK;
+}
+
+// everybody's counts of this slot -> d_all (also the barrier: a rank's contribution leaves after its scatter kernel)
+int gather_counts(hj3d_comm* cm, int slot) {
+  hj3d_ctx* c = cm->ctx;
+  if (cm->nc) {
+    NCCL_TRY(nccl().AllGather(cm->d_cursor[slot], cm->d_all[slot], kMaxRanges, ncclUint64, cm->nc, c->stream));
+    return HJ3D_OK;
+  }
+  for (hj3d_comm* o : cm->group->ranks) {       // single process: wait for every rank's kernel, then copy its counts over
+    if (o != cm) CUDA_TRY(cudaStreamWaitEvent(c->stream, o->ev_scatter[slot], 0));
+    CUDA_TRY(cudaMemcpyAsync(cm->d_all[slot] + (size_t)o->rank * kMaxRanges, o->d_cursor[slot], kMaxRanges * 8, cudaMemcpyDefault, c->stream));
+  }
+  return HJ3D_OK;
+}
+
+int free_slot(hj3d_comm* cm, int slot) {
+  for (int r = 0; r < cm->world; ++r) {
+    if (cm->peer_is_ipc[slot][r] && cm->peer_recv[slot][r]) cudaIpcCloseMemHandle(cm->peer_recv[slot][r]);
+    cm->peer_recv[slot][r] = nullptr; cm->peer_is_ipc[slot][r] = false;
+  }
+  if (cm->recv[slot]) { cudaStreamSynchronize(cm->ctx->stream); cudaFree(cm->recv[slot]); }
+  cm->recv[slot] = nullptr; cm->recv_records[slot] = 0;
+  return HJ3D_OK;
+}
+
+int comm_alloc_state(hj3d_comm* cm) {
+  CUDA_TRY(cudaSetDevice(cm->ctx->device));
+  for (int s = 0; s < kSlots; ++s) {
+    CUDA_TRY(cudaMalloc((void**)&cm->d_cursor[s], kMaxRanges * 8));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_all[s], (size_t)cm->world * kMaxRanges * 8));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_pstart[s], (kMaxRanges + 1) * 8));
+    CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_scatter[s], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaMallocHost(&cm->h_pinned, (size_t)(cm->world + 1) * kMaxRanges * 8));
+  return HJ3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hj3d_comm_unique_id(void* id128) {
+  if (!id128) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!nccl().load()) return fail(HJ3D_ERR_UNSUPPORTED, nccl().err);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NCCL_TRY(nccl().GetUniqueId((ncclUniqueId*)id128));
+  return HJ3D_OK;
+}
+
+int hj3d_comm_create(hj3d_ctx* c, int world, int rank, const void* id128, hj3d_comm** out) {
+  if (!c || !out || world < 1 || rank < 0 || rank >= world || world > kMaxPeers) return fail(HJ3D_ERR_INVALID, "bad comm arguments");
+  *out = nullptr;
+  if (world > 1 && !id128) return fail(HJ3D_ERR_INVALID, "id128 == NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  auto cm = std::make_unique<hj3d_comm>();
+  cm->ctx = c; cm->world = world; cm->rank = rank;
+  if (world > 1) {
+    if (!nccl().load()) return fail(HJ3D_ERR_UNSUPPORTED, nccl().err);
+    ncclUniqueId id; memcpy(&id, id128, sizeof id);
+    NCCL_TRY(nccl().CommInitRank(&cm->nc, world, id, rank));
+  } else {
+    cm->group = std::make_shared<LocalGroup>();
+    cm->group->ranks.push_back(cm.get());
+  }
+  HJ_TRY(comm_alloc_state(cm.get()));
+  *out = cm.release();
+  return HJ3D_OK;
+}
+
+int hj3d_comm_create_local(hj3d_ctx** ctxs, int world, hj3d_comm** out) {
+  if (!ctxs || !out || world < 1 || world > kMaxPeers) return fail(HJ3D_ERR_INVALID, "bad comm arguments");
+  auto group = std::make_shared<LocalGroup>();
+  std::vector<std::unique_ptr<hj3d_comm>> v;
+  for (int r = 0; r < world; ++r) {
+    if (!ctxs[r]) return fail(HJ3D_ERR_INVALID, "ctx == NULL");
+    auto cm = std::make_unique<hj3d_comm>();
+    cm->ctx = ctxs[r]; cm->world = world; cm->rank = r; cm->group = group;
+    HJ_TRY(comm_alloc_state(cm.get()));
+    v.push_back(std::move(cm));
+  }
+  for (int a = 0; a < world; ++a)                      // peer access between distinct devices of the group
+    for (int b = 0; b < world; ++b) {
+      const int da = ctxs[a]->device, db = ctxs[b]->device;
+      if (da == db) continue;
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, da, db));
+      if (!can) return fail(HJ3D_ERR_UNSUPPORTED, "devices of the local group cannot access each other's memory");
+      CUDA_TRY(cudaSetDevice(da));
+      cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(HJ3D_ERR_CUDA, cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  for (int r = 0; r < world; ++r) { group->ranks.push_back(v[r].get()); out[r] = v[r].release(); }
+  return HJ3D_OK;
+}
+
+int hj3d_comm_set_option(hj3d_comm* cm, int opt, int64_t v) {
+  if (!cm) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  switch (opt) {
+    case HJ3D_XOPT_TARGET_RANGES: if (v >= 1 && v <= (int64_t)kMaxRanges) cm->target_ranges = v; break;
+    case HJ3D_XOPT_MIN_RANGE_WIDTH: if (v >= 1) cm->min_width = v; break;
+    default: return fail(HJ3D_ERR_INVALID, "unknown comm option");
+  }
+  return HJ3D_OK;
+}
+
+int hj3d_comm_destroy(hj3d_comm* cm) {
+  if (!cm) return HJ3D_OK;
+  cudaSetDevice(cm->ctx->device);
+  cudaStreamSynchronize(cm->ctx->stream);
+  for (int s = 0; s < kSlots; ++s) {
+    free_slot(cm, s);
+    cudaFree(cm->d_cursor[s]); cudaFree(cm->d_all[s]); cudaFree(cm->d_pstart[s]);
+    if (cm->ev_scatter[s]) cudaEventDestroy(cm->ev_scatter[s]);
+  }
+  if (cm->h_pinned) cudaFreeHost(cm->h_pinned);
+  if (cm->nc) nccl().CommDestroy(cm->nc);
+  if (cm->group) { auto& r = cm->group->ranks; for (auto& p : r) if (p == cm) p = nullptr; }
+  delete cm;
+  return HJ3D_OK;
+}
+
+// Collective: (re)allocate this rank's receive buffer of `slot` and map every peer's.
+int hj3d_comm_reserve(hj3d_comm* cm, int slot, uint64_t records, uint32_t key_bytes) {
+  if (!cm || slot < 0 || slot >= kSlots || (key_bytes != 4 && key_bytes != 8)) return fail(HJ3D_ERR_INVALID, "bad reserve arguments");
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t rb = key_bytes == 8 ? 16 : 8;
+  HJ_TRY(free_slot(cm, slot));
+  if (records < 1024) records = 1024;
+  HJ_TRY(raw_alloc(&cm->recv[slot], records * rb));
+  cm->recv_records[slot] = records; cm->rec_bytes[slot] = rb;
+  if (cm->nc) {
+    // exchange CUDA IPC handles through the communicator itself: 64 bytes per rank
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine, cm->recv[slot]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    unsigned char* d_h = (unsigned char*)cm->d_all[slot];                 // staging: world * 64 bytes fit easily
+    unsigned char* d_m = (unsigned char*)cm->d_cursor[slot];
+    CUDA_TRY(cudaMemcpyAsync(d_m, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(nccl().AllGather(d_m, d_h, 64, ncclUint8, cm->nc, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(cm->world);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d_h, (size_t)cm->world * 64, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < cm->world; ++r) {
+      if (r == cm->rank) { cm->peer_recv[slot][r] = cm->recv[slot]; continue; }
+      void* p = nullptr;
+      CUDA_TRY(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+      cm->peer_recv[slot][r] = p; cm->peer_is_ipc[slot][r] = true;
+    }
+  } else {
+    // single process: every rank of the group sees every buffer; (re)publish to all members that exist
+    for (hj3d_comm* o : cm->group->ranks) {
+      if (!o) continue;
+      o->peer_recv[slot][cm->rank] = cm->recv[slot];
+      cm->peer_recv[slot][o->rank] = o->recv[slot];
+    }
+  }
+  return HJ3D_OK;
+}
+
+int hj3d_comm_shard(hj3d_comm* cm, uint64_t D, uint64_t* lo, uint64_t* hi) {
+  if (!cm || !D || D > 0xFFFFFFFFull || !lo || !hi) return fail(HJ3D_ERR_INVALID, "bad shard arguments");
+  const ExchangePlan p = make_plan(cm, D);
+  *lo = p.lo(cm->rank); *hi = p.hi(cm->rank);
+  return HJ3D_OK;
+}
+
+int hj3d_exchange_begin(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
+                        uint32_t flags) {
+  if (!cm || slot < 0 || slot >= kSlots) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
+  if (!D || D > 0xFFFFFFFFull) return fail(HJ3D_ERR_INVALID, "bad num_buckets");
+  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
+  if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 tuples per rank");
+  HJ_TRY(check_keyspec(ks));
+  hj3d_ctx* c = cm->ctx;
+  const uint32_t rb = ks.key_bytes == 8 ? 16 : 8;
+  if (!cm->recv[slot] || cm->rec_bytes[slot] != rb) return fail(HJ3D_ERR_INVALID, "hj3d_comm_reserve has not been called for this slot / key width");
+  for (int r = 0; r < cm->world; ++r) if (!cm->peer_recv[slot][r]) return fail(HJ3D_ERR_INVALID, "a peer has not reserved its receive buffer yet");
+  CUDA_TRY(cudaSetDevice(c->device));
+  ExchangePlan& pl = cm->plan[slot];
+  pl = make_plan(cm, D);
+  cm->ks[slot] = ks; cm->n_local[slot] = n; cm->exact[slot] = (flags & HJ3D_XCHG_EXACT) != 0;
+  // uniform regions: every (owned range, source) pair gets the same share of the owner's buffer
+  uint64_t min_recv = cm->recv_records[slot];
+  if (cm->group) for (hj3d_comm* o : cm->group->ranks) if (o && o->recv_records[slot] < min_recv) min_recv = o->recv_records[slot];
+  cm->cap_seg[slot] = (min_recv / ((uint64_t)pl.rpo * cm->world)) & ~1ull;
+  if (!cm->exact[slot] && cm->cap_seg[slot] < 2) return fail(HJ3D_ERR_INVALID, "receive buffer too small for the range x source regions");
+  Src src = make_src(d_tuples, n, ks, nullptr);
+  PhaseTimer pt(c, PH_PARTITION);
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
+  int rc = HJ3D_OK;
+  if (!cm->exact[slot]) {
+    k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, c->stream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
+    ++c->launches;
+    switch (ks.hash_id) {
+      case HJ3D_HASH_MURMUR32: rc = launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
+      case HJ3D_HASH_MURMUR64: rc = launch_scatter<HJ3D_HASH_MURMUR64>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
+      default:                 rc = launch_scatter<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
+    }
+  } else {
+    switch (ks.hash_id) {
+      case HJ3D_HASH_MURMUR32: rc = launch_hist<HJ3D_HASH_MURMUR32>(cm, slot, src); break;
+      case HJ3D_HASH_MURMUR64: rc = launch_hist<HJ3D_HASH_MURMUR64>(cm, slot, src); break;
+      default:                 rc = launch_hist<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src); break;
+    }
+  }
+  if (rc < 0) return rc;
+  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
+  if (cm->nc) HJ_TRY(gather_counts(cm, slot));       // multi-process: enqueue the all-gather right behind the kernel
+  cm->pending[slot] = true;
+  // exact mode keeps what it needs for the second pass
+  if (cm->exact[slot]) { cm->ks[slot] = ks; }
+  (void)rowid_base;
+  return HJ3D_OK;
+}
+
+// second pass of the exact mode: offsets from the gathered histogram, scatter, barrier
+static int exact_second_pass(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t rowid_base, unsigned long long* h_all) {
+  hj3d_ctx* c = cm->ctx;
+  const ExchangePlan& pl = cm->plan[slot];
+  CUDA_TRY(cudaMemcpyAsync(h_all, cm->d_all[slot], (size_t)cm->world * kMaxRanges * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  unsigned long long* h_ps = h_all + (size_t)cm->world * kMaxRanges;
+  uint64_t worst = 0;
+  for (int o = 0; o < cm->world; ++o) {                // owner o's buffer: ranges in order, sources in order, tightly packed
+    unsigned long long run = 0;
+    for (uint32_t p = 0; p < pl.owned(o); ++p) {
+      const uint32_t q = o * pl.rpo + p;
+      for (int s = 0; s < cm->world; ++s) { if (s == cm->rank) h_ps[q] = run; run += h_all[(size_t)s * kMaxRanges + q]; }
+    }
+    if (run > worst) worst = run;
+  }
+  uint64_t min_recv = cm->recv_records[slot];
+  if (cm->group) for (hj3d_comm* o : cm->group->ranks) if (o && o->recv_records[slot] < min_recv) min_recv = o->recv_records[slot];
+  if (worst > min_recv) return fail(HJ3D_ERR_NOMEM, "receive buffer too small for the exact exchange (a rank would receive " + std::to_string(worst) + " records)");
+  h_ps[pl.n_ranges] = 0;
+  CUDA_TRY(cudaMemcpyAsync(cm->d_pstart[slot], h_ps, ((size_t)pl.n_ranges + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
+  Src src = make_src(d_tuples, cm->n_local[slot], cm->ks[slot], nullptr);
+  int rc;
+  switch (cm->ks[slot].hash_id) {
+    case HJ3D_HASH_MURMUR32: rc = launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, ~0ull); break;
+    case HJ3D_HASH_MURMUR64: rc = launch_scatter<HJ3D_HASH_MURMUR64>(cm, slot, src, rowid_base, ~0ull); break;
+    default:                 rc = launch_scatter<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src, rowid_base, ~0ull); break;
+  }
+  if (rc < 0) return rc;
+  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
+  return HJ3D_OK;
+}
+
+int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t rowid_base, uint64_t rowid_bound, hj3d_parts** out) {
+  if (!cm || slot < 0 || slot >= kSlots || !out) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
+  if (!cm->pending[slot]) return fail(HJ3D_ERR_INVALID, "hj3d_exchange_begin has not been called for this slot");
+  *out = nullptr;
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const ExchangePlan& pl = cm->plan[slot];
+  unsigned long long* h_all = (unsigned long long*)cm->h_pinned;
+  if (!cm->nc) HJ_TRY(gather_counts(cm, slot));
+  if (cm->exact[slot]) {
+    if (cm->group && cm->group->ranks.size() > 1)
+      return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_EXACT needs one process per rank (or a group of one): the second pass is a collective");
+    HJ_TRY(exact_second_pass(cm, slot, d_tuples, rowid_base, h_all));
+    // barrier: everybody's second pass is done before anybody reads (the gathered cursors are not needed)
+    unsigned long long* scratch = cm->d_all[slot] + (size_t)cm->world * kMaxRanges - cm->world;   // tail of d_all is free: world <= 16
+    if (cm->nc) NCCL_TRY(nccl().AllGather(cm->d_cursor[slot], scratch, 1, ncclUint64, cm->nc, c->stream));
+  }
+  const uint32_t n_owned = pl.owned(cm->rank), n_seg = n_owned * cm->world;
+  auto parts = std::make_unique<hj3d_parts>();
+  parts->recs = cm->recv[slot]; parts->key_bytes = cm->ks[slot].key_bytes; parts->hash_id = cm->ks[slot].hash_id;
+  parts->D = pl.D; parts->bucket_lo = pl.lo(cm->rank); parts->bucket_hi = pl.hi(cm->rank);
+  parts->n_ranges = n_owned; parts->n_src = cm->world; parts->range_width = pl.width; parts->cap_seg = cm->cap_seg[slot];
+  parts->rowid_bound = rowid_bound;
+  CUDA_TRY(cudaMalloc((void**)&parts->d_start, ((size_t)n_seg + 1) * 8));
+  CUDA_TRY(cudaMalloc((void**)&parts->d_count, ((size_t)n_seg + 1) * 8));
+  k_xchg_segments<<<1, 32, 0, c->stream>>>(cm->d_all[slot], kMaxRanges, cm->world, cm->rank * pl.rpo, n_owned, cm->cap_seg[slot], cm->exact[slot] ? 1 : 0,
+                                           parts->d_start, parts->d_count);
+  ++c->launches;
+  if (!cm->exact[slot]) CUDA_TRY(cudaMemcpyAsync(h_all, cm->d_all[slot], (size_t)cm->world * kMaxRanges * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  // host view: what I received, what I sent to others, overflow of any region anybody wrote (every rank sees all counts)
+  uint64_t recv = 0, sent = 0; int overflow = 0;
+  for (int s = 0; s < cm->world; ++s)
+    for (uint32_t q = 0; q < pl.n_ranges; ++q) {
+      const uint64_t cnt = h_all[(size_t)s * kMaxRanges + q];
+      const int owner = (int)(q >> pl.rpo_shift);
+      if (!cm->exact[slot] && cnt > cm->cap_seg[slot]) overflow = 1;
+      const uint64_t stored = (!cm->exact[slot] && cnt > cm->cap_seg[slot]) ? cm->cap_seg[slot] : cnt;
+      if (owner == cm->rank) recv += stored;
+      if (s == cm->rank && owner != cm->rank) sent += stored;
+    }
+  parts->n_total = recv; parts->n_sent_remote = sent; parts->overflow = overflow;
+  cm->pending[slot] = false;
+  *out = parts.release();
+  return overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_parts_info(hj3d_parts* p, uint64_t* n_records, uint64_t* n_sent_remote, uint64_t* bucket_lo, uint64_t* bucket_hi, int* overflow) {
+  if (!p) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (n_records) *n_records = p->n_total;
+  if (n_sent_remote) *n_sent_remote = p->n_sent_remote;
+  if (bucket_lo) *bucket_lo = p->bucket_lo;
+  if (bucket_hi) *bucket_hi = p->bucket_hi;
+  if (overflow) *overflow = p->overflow;
+  return HJ3D_OK;
+}
+
+int hj3d_parts_destroy(hj3d_parts* p) {
+  if (!p) return HJ3D_OK;
+  cudaFree(p->d_start); cudaFree(p->d_count);
+  delete p;
+  return HJ3D_OK;
+}
+
+}  // extern "C"

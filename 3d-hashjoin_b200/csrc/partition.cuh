@@ -30,14 +30,16 @@ struct PartFn {
   uint32_t shift;      // log2(width) if pow2
   uint32_t is_pow2;
   uint32_t lo;         // first bucket of the (shard) directory
+  uint32_t nl;         // buckets of the (shard) directory: tuples of other buckets belong to no partition
   __device__ __forceinline__ uint32_t operator()(uint32_t bucket) const {
     const uint32_t b = bucket - lo;
+    if (b >= nl) return 0xFFFFFFFFu;       // (the last partition may reach past the directory's end)
     return is_pow2 ? (b >> shift) : (b / width);
   }
 };
 
-inline PartFn make_partfn(uint32_t width, uint32_t lo) {
-  PartFn f; f.width = width; f.is_pow2 = (width & (width - 1)) == 0; f.shift = 0; f.lo = lo;
+inline PartFn make_partfn(uint32_t width, uint32_t lo, uint32_t nl) {
+  PartFn f; f.width = width; f.is_pow2 = (width & (width - 1)) == 0; f.shift = 0; f.lo = lo; f.nl = nl;
   while ((1u << f.shift) < width) ++f.shift;
   return f;
 }
@@ -82,14 +84,14 @@ k_part_hist(Src s, Dir d, PartFn pf, uint32_t n_parts, unsigned long long* __res
 }
 
 // part_start[p] = exclusive prefix of counts (single thread; n_parts <= 1024)
-__global__ void k_part_prefix(const unsigned long long* __restrict__ counts, uint32_t n_parts,
+static __global__ void k_part_prefix(const unsigned long long* __restrict__ counts, uint32_t n_parts,
                               unsigned long long* __restrict__ part_start) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     unsigned long long run = 0;
     for (uint32_t p = 0; p < n_parts; ++p) { part_start[p] = run; run += counts[p]; }
   }
 }
-__global__ void k_part_fixed_starts(uint32_t n_parts, unsigned long long cap, unsigned long long* __restrict__ part_start) {
+static __global__ void k_part_fixed_starts(uint32_t n_parts, unsigned long long cap, unsigned long long* __restrict__ part_start) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n_parts) part_start[p] = (unsigned long long)p * cap;
 }
@@ -132,12 +134,18 @@ template <class KeyT> inline size_t part_smem_bytes(uint32_t fan, int threads, b
 //                     retires ~0.5 lanes/clk -> ~7.6 ms per 2^30 records chip wide, measured);
 // RANK_MATCH = true : every warp owns a private histogram; lanes with the same partition are found with
 //                     __match_any_sync and the group's leader bumps the counter with a plain load/store.
-template <int HASH, bool LEFTID, bool RECS, int THREADS, bool RANK_MATCH>
+// PEER (multi-GPU exchange, exchange.cu): partition q belongs to owner q >> peer.owner_shift and its region lives in THAT
+// GPU's receive buffer peer.base[owner] (a peer-mapped pointer: the stores below travel over NVLink), at the offset
+// part_start[q]; `out` is unused.  The level-1 partition pass and the all-to-all are one kernel.
+constexpr int kMaxPeers = 16;
+struct PeerOut { void* base[kMaxPeers]; uint32_t owner_shift; };
+
+template <int HASH, bool LEFTID, bool RECS, int THREADS, bool RANK_MATCH, bool PEER = false>
 __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? HJ3D_PART_MINBLOCKS : 1)
 k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint32_t n_parts, uint32_t fan,
                uint32_t rowid_base, unsigned long long cap,
                const unsigned long long* __restrict__ part_start, unsigned long long* __restrict__ cursor,
-               Slot<typename HashT<HASH>::key_t>* __restrict__ out) {
+               Slot<typename HashT<HASH>::key_t>* __restrict__ out, PeerOut peer = PeerOut{}) {
   using KeyT = typename HashT<HASH>::key_t;
   using SlotT = Slot<KeyT>;
   constexpr int ITEMS = PartCfg<KeyT>::kItems, TILE = THREADS * ITEMS, WARPS = THREADS / 32;
@@ -246,7 +254,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
     }
   }
   };
-  if (d.is_pow2 && pf.is_pow2) rank_all([&](KeyT k) { return ((HashT<HASH>::hash_lo32(k) & d.pow2_mask) - pf.lo) >> pf.shift; });
+  if (d.is_pow2 && pf.is_pow2) rank_all([&](KeyT k) { const uint32_t b = (HashT<HASH>::hash_lo32(k) & d.pow2_mask) - pf.lo; return b < pf.nl ? b >> pf.shift : 0xFFFFFFFFu; });
   else                         rank_all([&](KeyT k) { return pf(HashT<HASH>::bucket(k, d)); });
   __syncthreads();
   if (RANK_MATCH) {  // per partition: warp counts -> exclusive prefix over warps (each warp's base), total -> hist
@@ -306,7 +314,8 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   // (a 32-bit index variant of this loop with a no-overflow fast path measured 0.5 ms SLOWER per 2^30 records)
   for (uint32_t k = threadIdx.x; k < kept; k += THREADS) {
     const uint32_t lp = pid[k];
-    if (k < klim[lp]) out[dst[lp] + k] = tile[k];
+    SlotT* o = PEER ? reinterpret_cast<SlotT*>(peer.base[(q0 + lp) >> peer.owner_shift]) : out;
+    if (k < klim[lp]) o[dst[lp] + k] = tile[k];
   }
 }
 
@@ -352,7 +361,7 @@ k_part_sample(Src s, const uint2* __restrict__ tilemap, uint32_t tile, uint32_t 
 }
 
 // caps[p] = max(uniform capacity, estimate + 3 % + 4 sigma + 1024); caps[n_parts] = 0 (scan sentinel)
-__global__ void k_plan_caps(const unsigned long long* __restrict__ counts_s, uint32_t n_parts, unsigned long long n_total,
+static __global__ void k_plan_caps(const unsigned long long* __restrict__ counts_s, uint32_t n_parts, unsigned long long n_total,
                             unsigned long long cap_uniform, unsigned long long* __restrict__ caps) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p > n_parts) return;
@@ -366,7 +375,7 @@ __global__ void k_plan_caps(const unsigned long long* __restrict__ counts_s, uin
 }
 
 // out[0] = 1 if some partition received more records than its planned region holds, out[1] = records kept
-__global__ void k_part_overflow(const unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ part_start,
+static __global__ void k_part_overflow(const unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ part_start,
                                 uint32_t n_parts, unsigned long long* out) {
   unsigned long long over = 0, sum = 0;
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_parts; p += gridDim.x * blockDim.x) {
@@ -405,7 +414,7 @@ inline cudaError_t launch_part_scatter(cudaStream_t st, bool recs, int threads, 
 
 // ---- tile maps: block -> (first record, count) over partition regions with gaps --------------------
 // tile_prefix[p] = number of tiles of partitions < p;  tile_prefix[n_parts] = total (single block)
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 k_tile_prefix(const unsigned long long* __restrict__ counts, uint32_t n_parts, uint32_t tile, uint32_t* __restrict__ tile_prefix) {
   __shared__ uint32_t sm[33];
   uint32_t carry = 0;
@@ -420,7 +429,7 @@ k_tile_prefix(const unsigned long long* __restrict__ counts, uint32_t n_parts, u
   if (threadIdx.x == 0) tile_prefix[n_parts] = carry;
 }
 // grid = n_parts blocks
-__global__ void k_make_tilemap(const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
+static __global__ void k_make_tilemap(const unsigned long long* __restrict__ part_start, const unsigned long long* __restrict__ counts,
                                const uint32_t* __restrict__ tile_prefix, uint32_t tile, uint2* __restrict__ tilemap,
                                uint32_t* __restrict__ tile_part /* nullable: partition of every tile */) {
   const uint32_t p = blockIdx.x;
@@ -435,7 +444,7 @@ __global__ void k_make_tilemap(const unsigned long long* __restrict__ part_start
 }
 
 // work list over an unpartitioned input: chunk i = records [i*chunk, ..), all in fine partition 0
-__global__ void k_make_chunks(uint64_t n, uint32_t chunk, uint32_t n_chunks, uint2* __restrict__ work, uint32_t* __restrict__ work_part) {
+static __global__ void k_make_chunks(uint64_t n, uint32_t chunk, uint32_t n_chunks, uint2* __restrict__ work, uint32_t* __restrict__ work_part) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_chunks) return;
   const uint64_t st = (uint64_t)i * chunk, left = n - st;
@@ -443,7 +452,7 @@ __global__ void k_make_chunks(uint64_t n, uint32_t chunk, uint32_t n_chunks, uin
   work_part[i] = 0;
 }
 
-__global__ void k_fixed_starts_u64(uint32_t n, unsigned long long cap, unsigned long long* __restrict__ st) {
+static __global__ void k_fixed_starts_u64(uint32_t n, unsigned long long cap, unsigned long long* __restrict__ st) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < n) st[p] = (unsigned long long)p * cap;
 }

@@ -66,6 +66,9 @@ extern "C" {
 #define HJ3D_OPT_SMEM_BUILD_BYTES 13 /* shared memory budget of one build range (default 64 KiB)               */
 #define HJ3D_OPT_PROBE_THREADS   11 /* shared-memory probe block size: 256 or 512 (default 256)                  */
 #define HJ3D_OPT_LEAN_PROBE      18 /* 0/1: unique / nested probes of fine partitions use the lean kernel (default 1)  */
+#define HJ3D_OPT_PACKED_PROBE    21 /* 0/1: unique chaining probes of large inputs run over compressed table slices (default 0) */
+#define HJ3D_OPT_PACKED_MIN_PROBE 22 /* probe inputs smaller than this use the other paths (default 2^22)                     */
+#define HJ3D_OPT_PACKED_SLICE_BYTES 23 /* shared memory of one compressed-slice probe block (default 100 KiB; tests shrink it) */
 #define HJ3D_OPT_UNNEST_HOT_CAP  19 /* entries of the unnest's hot-tuple list (default 2^20; tests shrink it)           */
 #define HJ3D_OPT_PART_SAMPLE     20 /* partition regions sized from a sampled histogram: 0 never, 1 after this ctx has seen
                                        an overflow (default), 2 always                                                */
@@ -157,6 +160,10 @@ int hj3d_iota_u32(hj3d_ctx* ctx, uint32_t* d_dst, uint64_t n, uint32_t first);
 int hj3d_table_create(hj3d_ctx* ctx, int kind, uint64_t num_buckets, hj3d_table** out);
 int hj3d_table_build(hj3d_ctx* ctx, hj3d_table* t, const void* d_tuples, uint64_t n, hj3d_keyspec ks);
 int hj3d_table_clear(hj3d_ctx* ctx, hj3d_table* t);
+/* promise for build tuples that carry their own row id (rowid_offset != HJ3D_NO_ROWID, e.g. exchanged (key, global row id)
+ * records): every row id is < bound.  Lets the engine pack (hash quotient, row id) into one 32-bit slot in shared memory;
+ * 0 = unknown (default).  Takes effect at the next hj3d_table_build. */
+int hj3d_table_set_rowid_bound(hj3d_ctx* ctx, hj3d_table* t, uint64_t bound);
 int hj3d_table_destroy(hj3d_ctx* ctx, hj3d_table* t);
 int hj3d_table_stats(hj3d_ctx* ctx, hj3d_table* t, hj3d_stats* out);
 int hj3d_table_size(hj3d_table* t, uint64_t* num_entries, uint64_t* num_groups); /* size(); #MainNodes */
@@ -226,9 +233,56 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
                    hj3d_counters* probe_out, hj3d_counters* unnest_out, hj3d_stats* stats_out);
 
 /* ---- multi-GPU sharding (no reference equivalent) ---------------------------
- * owner(tuple) = bucket(tuple) / ceil(num_buckets / n_owners): contiguous bucket ranges, so every
- * bucket (chain, key group) lives on exactly one GPU.  Writes (key, global row id) pairs grouped by
- * owner into d_out (key_bytes + 4 bytes each, 8 or 16 byte records) and the per-owner counts
+ * The join shards by bucket range: owner(tuple) is a function of bucket(tuple), so every bucket (chain, key group) lives
+ * on exactly one GPU, counters add, checksums add / xor and HtStatistics merge exactly (hj3d_stats_merge).
+ *
+ * hj3d_exchange_* is the data plane.  The exchange IS partition level 1 of the engine: each rank partitions its slice of
+ * a relation into coarse bucket ranges and the partition kernel stores every range directly into the receive buffer of
+ * the GPU that owns it (peer-mapped memory: the stores cross NVLink as the kernel writes them); one small all-gather of
+ * the per-(source, range) counts is the only collective and also the barrier.  The result (hj3d_parts) is the
+ * coarse-partitioned input of the local join: hj3d_table_build_parts / hj3d_probe_parts continue at partition level 2,
+ * with no host round trip and no further pass over the received data in between.
+ *
+ * Communicators:
+ *   one process per GPU : rank 0 calls hj3d_comm_unique_id, the host code distributes the 128 bytes (MPI, torch.distributed,
+ *                         a file), every rank calls hj3d_comm_create.  NCCL carries the count all-gather, CUDA IPC maps the
+ *                         peers' receive buffers.
+ *   one process, N GPUs : hj3d_comm_create_local(ctxs, N, comms) -- what a C++ driver holding all contexts uses.  Call
+ *                         hj3d_exchange_begin for every rank first, then hj3d_exchange_end for every rank.
+ * slot: 0 or 1 -- two relations (build side, probe side) can be in flight at once.
+ * Records carry (key, global row id) with global row id = rowid_base + position in the local slice.
+ * flags: HJ3D_XCHG_EXACT = two passes (histogram first, regions packed at exact offsets): for skewed keys whose ranges
+ *        overflow the uniform regions (hj3d_exchange_end returns HJ3D_OVERFLOW then; nothing is lost by retrying). */
+#define HJ3D_XCHG_EXACT 1u
+#define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256) */
+#define HJ3D_XOPT_MIN_RANGE_WIDTH 2 /* smallest range width in buckets (default 16384: a multiple of every fine-partition width) */
+typedef struct hj3d_comm  hj3d_comm;
+typedef struct hj3d_parts hj3d_parts;
+int hj3d_comm_unique_id(void* id128);
+int hj3d_comm_create(hj3d_ctx* ctx, int world, int rank, const void* id128, hj3d_comm** out);
+int hj3d_comm_create_local(hj3d_ctx** ctxs, int world, hj3d_comm** out_comms);
+int hj3d_comm_set_option(hj3d_comm* comm, int option, int64_t value);
+int hj3d_comm_destroy(hj3d_comm* comm);
+/* collective: (re)allocate this rank's receive buffer of `slot` for `records` records of key_bytes + 4 bytes and map the peers' */
+int hj3d_comm_reserve(hj3d_comm* comm, int slot, uint64_t records, uint32_t key_bytes);
+/* bucket range [lo, hi) this rank owns in a num_buckets wide directory: create its table with hj3d_table_create_shard */
+int hj3d_comm_shard(hj3d_comm* comm, uint64_t num_buckets, uint64_t* lo, uint64_t* hi);
+int hj3d_exchange_begin(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
+                        uint32_t rowid_base, uint32_t flags);
+/* d_tuples / rowid_base: the same as in _begin (the exact mode reads the slice a second time); rowid_bound: global relation
+ * size (0 = unknown).  Returns HJ3D_OVERFLOW if a region overflowed anywhere (every rank returns it). */
+int hj3d_exchange_end(hj3d_comm* comm, int slot, const void* d_tuples, uint32_t rowid_base, uint64_t rowid_bound, hj3d_parts** out);
+int hj3d_parts_info(hj3d_parts* parts, uint64_t* n_records, uint64_t* n_sent_remote, uint64_t* bucket_lo, uint64_t* bucket_hi, int* overflow);
+int hj3d_parts_destroy(hj3d_parts* parts);
+/* hj3d_table_build / hj3d_probe_chaining (mode 0, 1 = IsBuildKeyUnique) / hj3d_probe_nested (2) / hj3d_probe_nested_unnest (3)
+ * on an exchanged relation; the table must be the shard hj3d_comm_shard names.  `left` ids are global row ids. */
+int hj3d_table_build_parts(hj3d_ctx* ctx, hj3d_table* t, hj3d_parts* parts);
+int hj3d_probe_parts(hj3d_ctx* ctx, hj3d_table* t, hj3d_parts* parts, int mode, uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap,
+                     hj3d_counters* probe_out, hj3d_counters* unnest_out);
+
+/* Lower-level pieces (kept: callers that move the records themselves, e.g. over another transport).
+ * owner(tuple) = bucket(tuple) / ceil(num_buckets / n_owners): contiguous bucket ranges.  Writes (key, global row id) pairs
+ * grouped by owner into d_out (key_bytes + 4 bytes each, 8 or 16 byte records) and the per-owner counts
  * (host array of n_owners).  rowid_base is added to the local row position. */
 int hj3d_partition_by_owner(hj3d_ctx* ctx, const void* d_tuples, uint64_t n, hj3d_keyspec ks,
                             uint64_t num_buckets, uint32_t n_owners, uint32_t rowid_base,

@@ -39,8 +39,9 @@ def pkg():
 def ctx(pkg, request):
     """Every GPU test runs on four engine configurations: in place with global-memory lookups (small inputs),
     bucket-range partitioned with L2-window lookups, partitioned into fine partitions probed in shared memory
-    (what large inputs take; the latter two forced on at test sizes), and the DEFAULT options (whatever path the
-    engine picks for the input size, which is what the headline configuration runs)."""
+    (what large inputs take; the latter two forced on at test sizes), and the default options with the
+    compressed-slice probe of large unique-key probes forced on at test sizes (tests/test_gpu_parity_large.py runs the
+    untouched defaults at full size)."""
     import torch
     assert torch.cuda.is_available()
     # same stream as torch, so tensor fills / copies and engine kernels are ordered
@@ -64,5 +65,11 @@ def ctx(pkg, request):
         c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096)
         c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
         c.set_option(pkg.capi.OPT_PART_SAMPLE, 2)            # regions planned from a sampled histogram (what skewed inputs take)
+    if request.param == "default":
+        # default options, except that the compressed-slice probe (what 2^22+ row probe sides take) is forced on with
+        # small slices, so that several fine partitions, two partition levels and slices that do not fit all occur
+        c.set_option(pkg.capi.OPT_PACKED_PROBE, 1)
+        c.set_option(pkg.capi.OPT_PACKED_MIN_PROBE, 0)
+        c.set_option(pkg.capi.OPT_PACKED_SLICE_BYTES, 4096)
     c.mode = request.param
     return c

@@ -404,3 +404,78 @@ def test_shard_table_built_from_an_unpartitioned_relation(pkg, ctx, oracle):
             assert merged.as_dict() == o["stats"], what
             assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"], what
             assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"])), what
+
+
+@pytest.mark.parametrize("world", [1, 3, 4])
+def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world):
+    """The multi-GPU data plane (csrc/exchange.cu) with all ranks in ONE process on one device (hj3d_comm_create_local):
+    every rank partitions its slice of both relations by bucket range straight into the owners' receive buffers, builds
+    its shard from what it received (hj3d_table_build_parts: the local join continues at partition level 2) and probes
+    it; merged counters, statistics and the result multiset equal the unsharded reference result.  Small range widths
+    and engine thresholds force the fine-partition path, the compaction fallback and ranks that own nothing."""
+    import torch
+    import ctypes as C
+    lib = pkg.capi.load()
+    rng = np.random.default_rng(100 + world)
+    stream = torch.cuda.current_stream().cuda_stream
+    for (nR, nS, D, width, fine) in ((40000, 130000, 40000, 1024, True), (3000, 9000, 1500, 256, False), (60000, 100000, 7001, 64, True)):
+        R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+        S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR, nS)
+        ctxs = [pkg.Context(0, stream=stream) for _ in range(world)]
+        for c in ctxs:
+            if fine:   # force the shared-memory fine-partition paths at test sizes
+                c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0); c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
+                c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096); c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
+        comms = pkg.Comm.local(ctxs)
+        for cm in comms:
+            cm.set_option(pkg.capi.XOPT_MIN_RANGE_WIDTH, width)
+            cm.set_option(pkg.capi.XOPT_TARGET_RANGES, 64)
+        for mode in (1, 0, 3):
+            B, kb, P, kp = (R, 0, S, 4) if mode == 1 else (S, 4, R, 0)
+            o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(12, kb), D, P, pyo.KeySpec(12, kp))
+            nB, nP = len(B), len(P)
+            sl = lambda n, r: (r * n // world, (r + 1) * n // world)
+            for cm in comms:
+                cm.reserve(0, int(nB * 1.5 / world) + 70000, 4)
+                cm.reserve(1, int(nP * 1.5 / world) + 70000, 4)
+            dB, dP = to_dev(B), to_dev(P)
+            vB, vP = dB.view(-1, 12), dP.view(-1, 12)
+            slices = []
+            for r, cm in enumerate(comms):                   # begin for every rank first, then end for every rank
+                b0, b1 = sl(nB, r); p0, p1 = sl(nP, r)
+                tb, tp = vB[b0:b1].contiguous(), vP[p0:p1].contiguous()
+                slices.append((tb, b0, b1, tp, p0, p1))
+                cm.begin(0, tb, b1 - b0, KSg(pkg, 12, kb), D, b0)
+                cm.begin(1, tp, p1 - p0, KSg(pkg, 12, kp), D, p0)
+            parts = (pkg.Stats * world)()
+            tot = {"matches": 0, "num_cmps": 0}
+            pairs, n_recv = [], 0
+            for r, cm in enumerate(comms):
+                tb, b0, b1, tp, p0, p1 = slices[r]
+                rc, pb = cm.end(0, tb, b0, nB); assert rc == 0
+                rc, pp = cm.end(1, tp, p0, nP); assert rc == 0
+                n_recv += pb.info()["n_records"]
+                lo, hi = cm.shard(D)
+                assert (lo, hi) == (pb.info()["bucket_lo"], pb.info()["bucket_hi"])
+                t = ctxs[r].table(pkg.CHAINING if mode <= 1 else pkg.NESTED, D, shard=(lo, hi))
+                t.build_parts(pb)
+                _, c0, u0 = t.probe_parts(pp, mode, flags=pkg.F_CHECKSUM)                        # count only
+                n_out = (u0 if mode == 3 else c0)["out_tuples"]
+                out = torch.zeros((max(n_out, 1), 2), dtype=torch.int32, device="cuda")
+                _, c1, u1 = t.probe_parts(pp, mode, flags=pkg.F_CHECKSUM, out=out, out_cap=n_out)
+                assert (c1["matches"], c1["num_cmps"]) == (c0["matches"], c0["num_cmps"])
+                pairs.append(out[:(u1 if mode == 3 else c1)["out_written"]].cpu().numpy().view(np.uint32))
+                tot["matches"] += c1["matches"]; tot["num_cmps"] += c1["num_cmps"]
+                parts[r] = pkg.Stats(**t.stats())
+                t.destroy(); pb.destroy(); pp.destroy()
+            what = f"exchange world={world} shape={(nR, nS, D, width)} mode={mode}"
+            assert n_recv == nB, what
+            merged = pkg.Stats()
+            lib.hj3d_stats_merge(parts, world, C.byref(merged))
+            assert merged.as_dict() == o["stats"], what
+            assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"], what
+            assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"])), what
+        for cm in comms:
+            cm.destroy()
+        for c in ctxs:
+            c.close()
