@@ -80,6 +80,11 @@ class Context:
                                                     _ptr(out), counts))
         return [int(x) for x in counts]
 
+    def gen_column(self, tuples, tuple_bytes, offset, first_row, n, kind, vmax=1, zipf_q=0.0, shift=0, seed=0):
+        """device-side generation of one uint32 attribute of a row store (hj3d_gen_column_u32)"""
+        capi.check(self.lib.hj3d_gen_column_u32(self.h, _ptr(tuples), tuple_bytes, offset, int(first_row), int(n), kind, int(vmax),
+                                                float(zipf_q), int(shift), int(seed)))
+
     def probe2_unnest2(self, table_s, table_t, tuples, n, ks, flags=F_CHECKSUM, want_triples=False, out=None, out_cap=0):
         """exp4's Ndu probe strand as one device pipeline (hj3d_probe2_unnest2): returns (rc, [4 counter dicts], triples, n_out).
         want_triples: run once count-only to size the result, then materialise (r, s, t) row-id triples in a torch tensor."""

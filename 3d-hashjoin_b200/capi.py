@@ -22,6 +22,7 @@ OPT_PART_THREADS, OPT_PART_RANK_MATCH, OPT_PROBE_THREADS, OPT_SMEM_BUILD, OPT_SM
 OPT_LEAN_PROBE = 18
 OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
 OPT_PACKED_PROBE, OPT_PACKED_MIN_PROBE, OPT_PACKED_SLICE_BYTES = 21, 22, 23
+GEN_IOTA, GEN_PERMUTATION, GEN_UNIFORM, GEN_ZIPF, GEN_CONST = 0, 1, 2, 3, 4
 XCHG_EXACT = 1
 XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH = 1, 2
 
@@ -38,6 +39,7 @@ SYMBOLS = [
     "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
     "hj3d_table_build_parts", "hj3d_probe_parts",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
+    "hj3d_gen_column_u32",
     "hj3d_mem_alloc", "hj3d_mem_free", "hj3d_memcpy_h2d", "hj3d_memcpy_d2h", "hj3d_iota_u32",
 ]
 
@@ -75,7 +77,8 @@ class Stats(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("partition_ms", "histogram_ms", "scan_ms", "scatter_ms", "group_ms",
-                                         "probe_ms", "unnest_ms", "total_ms")] + [("kernel_launches", C.c_uint64)]
+                                         "probe_ms", "unnest_ms", "total_ms")] + [("kernel_launches", C.c_uint64),
+                                                                                          ("partition_l1_ms", C.c_float), ("reserved_", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -138,6 +141,7 @@ def load():
     L.hj3d_partition_by_owner.argtypes = [vp, vp, u64, KeySpec, u64, u32, u32, vp, C.POINTER(u64)]
     L.hj3d_owner_range.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_stats_merge.argtypes = [C.POINTER(Stats), u32, C.POINTER(Stats)]
+    L.hj3d_gen_column_u32.argtypes = [vp, vp, u32, u32, u64, u64, i32, u64, C.c_double, u64, u64]
     L.hj3d_mem_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     L.hj3d_mem_free.argtypes = [vp, vp]
     L.hj3d_memcpy_h2d.argtypes = [vp, vp, vp, u64]

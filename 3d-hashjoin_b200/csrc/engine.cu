@@ -186,7 +186,7 @@ int partition_local(hj3d_ctx* c, Src src, Dir d, uint32_t P, uint32_t width, uin
     return launch_part_scatter<HASH, LEFTID>(c->stream, recs, (int)c->part_threads, c->part_rank_match != 0, nb, src, nullptr, d, pf,
                                              P, P, rowid_base, cap_, out->part_start, cursor_, out->recs);
   };
-  CUDA_TRY(launch(planned ? 0ull : cap, out->counts));
+  { PhaseTimer p1(c, PH_PART1); CUDA_TRY(launch(planned ? 0ull : cap, out->counts)); }   // the level-1 scatter kernel alone (bench.py's roofline)
   c->launches += nb ? 2 : 1;
   unsigned long long* h = (unsigned long long*)c->h_pinned;               // P <= 1024 -> 8 KB counts + 8 KB starts
   CUDA_TRY(cudaMemcpyAsync(h, out->counts, (size_t)P * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1079,6 +1079,7 @@ int hj3d_ctx_timings(hj3d_ctx* c, hj3d_timings* out) {
   }
   out->partition_ms = v[PH_PARTITION]; out->histogram_ms = v[PH_HIST]; out->scan_ms = v[PH_SCAN];
   out->scatter_ms = v[PH_SCATTER]; out->group_ms = v[PH_GROUP]; out->probe_ms = v[PH_PROBE]; out->unnest_ms = v[PH_UNNEST];
+  out->partition_l1_ms = v[PH_PART1];
   out->total_ms = 0.f;
   cudaEventElapsedTime(&out->total_ms, c->ev_total[0], c->ev_total[1]);
   cudaGetLastError();

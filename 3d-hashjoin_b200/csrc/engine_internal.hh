@@ -26,7 +26,7 @@ static inline int fail(int code, const std::string& msg) { hj3d_err_slot() = msg
 #define HJ_TRY(expr) do { int _rc = (expr); if (_rc < 0) return _rc; } while (0)
 
 // ------------------------------------------------------------------------------------ objects
-enum Phase { PH_PARTITION, PH_HIST, PH_SCAN, PH_SCATTER, PH_GROUP, PH_PROBE, PH_UNNEST, PH_COUNT };
+enum Phase { PH_PARTITION, PH_HIST, PH_SCAN, PH_SCATTER, PH_GROUP, PH_PROBE, PH_UNNEST, PH_PART1, PH_COUNT };
 
 struct hj3d_ctx {
   int          device = 0;

@@ -5,17 +5,24 @@ main_experiment1 at the reference's largest shape (-R 27 -S 30: 2^27 build / 2^3
 materialised (probe row, build row) result pairs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--plan Csr|CsrUU|Nsr|Crs|Nrs]
-                    [--log2-build 27 --log2-probe 30]
+                    [--log2-build 27 --log2-probe 30] [--zipf S] [--config 3|4|5]
 
-One "step" = clear the table, build strand, probe strand (+ unnest for nested plans) over one batch of
-synthetic input resident in HBM.  N > 1 (torchrun): the same total workload is sharded by bucket range
-(strong scaling): every rank partitions its slice of both relations by owner, exchanges (key, global row
-id) records with an NCCL all-to-all, and joins its shard locally; partition + exchange are inside the
-timed region.  Prints ONE JSON line (rank 0).
+One "step" = clear the table, build strand, probe strand (+ unnest for nested plans) over one batch of synthetic
+input resident in HBM.  The relations are generated on the device by the engine's counter-based generators
+(csrc/datagen.cu): every value is a pure function of the global row id, so a run on N GPUs joins EXACTLY the data a run
+on one GPU joins (rank r holds rows [r*n/N, (r+1)*n/N) of both relations).
+
+N > 1 (torchrun): the same total workload is sharded by bucket range (strong scaling).  Every rank partitions its
+slices of both relations by bucket range straight into the owners' receive buffers over NVLink (hj3d_exchange_*: the
+exchange is partition level 1 of the local join), then builds and probes its shard; exchange and join are inside the
+timed region.  Results are verified at every N: the all-reduced result checksum against an independent torch
+computation, and count / numCmps / merged HtStatistics against the unsharded engine path run on rank 0 over the same
+data.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
@@ -29,6 +36,8 @@ PLANS = {  # plan -> (table kind, build relation, mode)   mode: 1 chaining uniqu
     "Csr": ("chaining", "R", 1), "CsrUU": ("chaining", "R", 0), "Nsr": ("nested", "R", 3),
     "Crs": ("chaining", "S", 0), "Nrs": ("nested", "S", 3),
 }
+SEED_R, SEED_S = 1234, 99
+M64 = (1 << 64) - 1
 
 
 def peaks():
@@ -91,102 +100,139 @@ def algorithmic_bytes(nB, nP, nM, nO, D, T=12, K=4, I=4, nested=False):
     return compulsory + table
 
 
-# ------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's own CPU implementation (oracle/_ref, the unmodified templates; else the C port) on a
-    bounded sample of the same workload shape: build 2^sb / probe 2^(sb+3), single thread (the reference has
-    no parallel path)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def workload_config(args, sample=None):
+    skew = "--no-skew" if args.zipf <= 0 else f"--skew (Zipf s={args.zipf} by rejection-inversion, device generated)"
+    w = (f"main_experiment1 key/foreign-key join -R {args.log2_build} -S {args.log2_probe} {skew} -t 0 -b 1, "
+         f"plan {args.plan}, uint32 keys, 12-byte row-store tuples, materialised result pairs")
+    cfg = {"workload": w, "plan": args.plan, "log2_build": args.log2_build, "log2_probe": args.log2_probe,
+           "l2_policy": "inputs (>= 1.6 GB + 12.9 GB) are far larger than the 126 MB L2; no flush needed",
+           "parallelism": f"bucket-range sharding over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU"}
+    if sample:
+        cfg["reference_sample"] = sample
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------ CPU legs (the checker, timed)
+def cpu_sample(args):
+    """A bounded sample of the workload for the CPU legs: the reference's OWN generator (Experiment1::init through
+    oracle/_ref) at -R sb -S sb+(S-R); numpy when the reference library is not there."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    kind_name, build_rel, mode = PLANS[args.plan]
     sb = args.ref_log2_build
-    nR, nS = 1 << sb, 1 << (sb + (args.log2_probe - args.log2_build))
-    rng = np.random.default_rng(1)
-    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR).astype(np.uint32)
-    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS, dtype=np.uint32); S[:, 1] = rng.integers(0, nR, nS, dtype=np.uint32)
-    use_ref = pyoracle.Ref.available()
-    impl = pyoracle.Ref() if use_ref else pyoracle.Oracle()
+    sp = sb + (args.log2_probe - args.log2_build)
+    if pyoracle.Ref.available():
+        ref = pyoracle.Ref()
+        R, S, dv = ref.gen_exp1(sb, sp, 1 if args.zipf > 0 else 0, 0)
+        gen = "Experiment1::init of the reference (oracle/_ref)" + (", --skew (the reference fixes s = 1)" if args.zipf > 0 else "")
+    else:
+        rng = np.random.default_rng(1)
+        nR, nS = 1 << sb, 1 << sp
+        R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR).astype(np.uint32)
+        S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS, dtype=np.uint32); S[:, 1] = rng.integers(0, nR, nS, dtype=np.uint32)
+        dv = len(np.unique(S[:, 1]))
+        gen = "numpy stand-in for the reference generator"
+    return pyoracle, R, S, int(dv), f"-R {sb} -S {sp} ({gen})"
+
+
+def cpu_join(pyoracle, plan, R, S, dv):
+    """one build strand + probe strand on the host: the unmodified reference templates when available, else the C port"""
+    kind_name, build_rel, mode = PLANS[plan]
     ksR, ksS = pyoracle.KeySpec(12, 0), pyoracle.KeySpec(12, 4)
     B, ksB, P, ksP = (R, ksR, S, ksS) if build_rel == "R" else (S, ksS, R, ksR)
-    D = nR if build_rel == "R" else max(len(np.unique(S[:, 1])), 1)
+    D = len(R) if build_rel == "R" else max(dv, 1)
     kind = pyoracle.CHAINING if kind_name == "chaining" else pyoracle.NESTED
-    times = []
+    if pyoracle.Ref.available():
+        t = pyoracle.Ref().build(kind, B, len(B), ksB, D, timed=True)
+        c, cu, _, ns = t.probe(P, len(P), ksP, mode, timing_top=True)
+        return (t.build_ns + ns) * 1e-9, "reference", c, cu, t.stats(), D
+    t0 = time.perf_counter()
+    t = pyoracle.Oracle().build(kind, B, len(B), ksB, D)
+    cu = None
+    if mode <= 1:
+        c, _ = t.probe_chaining(P, len(P), ksP, unique=(mode == 1), materialize=False)
+    else:
+        c, nest = t.probe_nested(P, len(P), ksP)
+        cu, _ = t.unnest(nest[:, 0], nest[:, 1])
+    return time.perf_counter() - t0, "port", c, cu, t.stats(), D
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (single thread: it has no parallel path) on a bounded
+    sample of the workload, generated by the reference's own generator; the sample is named in config."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    pyoracle, R, S, dv, sample = cpu_sample(args)
+    times, kind = [], "port"
     for it in range(args.warmup + args.steps):
-        if use_ref:
-            t = impl.build(kind, B, len(B), ksB, D, timed=True)
-            c, cu, _, ns = t.probe(P, len(P), ksP, mode, timing_top=True)
-            dt = (t.build_ns + ns) * 1e-9
-        else:
-            t0 = time.perf_counter()
-            t = impl.build(kind, B, len(B), ksB, D)
-            if mode <= 1:
-                t.probe_chaining(P, len(P), ksP, unique=(mode == 1), materialize=False)
-            else:
-                c, nest = t.probe_nested(P, len(P), ksP)
-                t.unnest(nest[:, 0], nest[:, 1])
-            dt = time.perf_counter() - t0
-        del t
+        dt, kind, _, _, _, _ = cpu_join(pyoracle, args.plan, R, S, dv)
         if it >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    value = (nR + nS) / (ms * 1e-3)
-    sample = f"plan {args.plan}, build 2^{sb} / probe 2^{sb + (args.log2_probe - args.log2_build)} of the same generator, 1 thread"
+    value = (len(R) + len(S)) / (ms * 1e-3)
+    desc = f"plan {args.plan}, {sample}, 1 thread, rate-normalised (tuples/s)"
     line = {"impl": "reference", "metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": "tuples/s", "cores": 1, "kind": "reference" if use_ref else "port",
-                             "sample": sample, "host_cores": os.cpu_count()},
+            "config": workload_config(args, sample=desc),
+            "cpu_baseline": {"value": value, "unit": "tuples/s", "cores": 1, "kind": kind, "sample": desc, "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    skew = "--no-skew" if args.zipf <= 0 else f"--skew (Zipf-like s={args.zipf}, device generated)"
-    return {"workload": f"main_experiment1 key/foreign-key join -R {args.log2_build} -S {args.log2_probe} {skew} -t 0 -b 1, "
-                        f"plan {args.plan}, uint32 keys, 12-byte row-store tuples, materialised result pairs",
-            "plan": args.plan, "log2_build": args.log2_build, "log2_probe": args.log2_probe,
-            "l2_policy": "inputs (>= 1.6 GB + 12.9 GB) are far larger than the 126 MB L2; no flush needed",
-            "parallelism": f"bucket-range sharding over {args.gpus} GPU(s)" if args.gpus > 1 else "single GPU"}
+def cpu_baseline_leg(args, pkg, ctx):
+    """Bounded sample on the box's host cores (rank 0, N=1 only); the SAME arrays then go through the GPU engine and
+    every counter is compared, so the baseline and the product demonstrably join the same relations."""
+    try:
+        import numpy as np
+        import torch
+        pyoracle, R, S, dv, sample = cpu_sample(args)
+        dt, kind, c, cu, st, D = cpu_join(pyoracle, args.plan, R, S, dv)
+        kind_name, build_rel, mode = PLANS[args.plan]
+        B, kb, P, kp = (R, 0, S, 4) if build_rel == "R" else (S, 4, R, 0)
+        dB = torch.from_numpy(B.view(np.int32)).cuda(); dP = torch.from_numpy(P.view(np.int32)).cuda()
+        t = ctx.table(pkg.CHAINING if kind_name == "chaining" else pkg.NESTED, D).build(dB, len(B), pkg.KeySpec(12, kb))
+        if mode <= 1:
+            _, gc = t.probe_chaining(dP, len(P), pkg.KeySpec(12, kp), unique=(mode == 1), flags=0)
+            same = (gc["matches"], gc["num_cmps"]) == (c["matches"], c["num_cmps"])
+        else:
+            _, gc, gu = t.probe_nested_unnest(dP, len(P), pkg.KeySpec(12, kp), flags=0)
+            same = (gc["matches"], gc["num_cmps"], gu["out_tuples"]) == (c["matches"], c["num_cmps"], cu["out_tuples"])
+        same = same and t.stats() == st
+        t.destroy()
+        return {"value": (len(R) + len(S)) / dt, "unit": "tuples/s", "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+                "sample": f"plan {args.plan}, {sample}, 1 repetition, 1 thread (the reference is single-threaded)", "seconds": dt,
+                "gpu_engine_agrees_on_the_same_arrays": bool(same)}
+    except Exception as e:  # the baseline is a reported side figure; never fail the bench for it
+        return {"value": None, "unit": "tuples/s", "cores": 1, "kind": "unavailable", "sample": repr(e)}
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def cpu_baseline_leg(args):
-    """Bounded sample of the same workload on the box's host cores (rank 0, N=1 only)."""
-    try:
-        import numpy as np
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import pyoracle
-        kind_name, build_rel, mode = PLANS[args.plan]
-        sb = args.ref_log2_build
-        nR, nS = 1 << sb, 1 << (sb + (args.log2_probe - args.log2_build))
-        rng = np.random.default_rng(1)
-        R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR).astype(np.uint32)
-        S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS, dtype=np.uint32); S[:, 1] = rng.integers(0, nR, nS, dtype=np.uint32)
-        ksR, ksS = pyoracle.KeySpec(12, 0), pyoracle.KeySpec(12, 4)
-        B, ksB, P, ksP = (R, ksR, S, ksS) if build_rel == "R" else (S, ksS, R, ksR)
-        D = nR if build_rel == "R" else max(len(np.unique(S[:, 1])), 1)
-        kind = pyoracle.CHAINING if kind_name == "chaining" else pyoracle.NESTED
-        if pyoracle.Ref.available():
-            ref = pyoracle.Ref()
-            t = ref.build(kind, B, len(B), ksB, D, timed=True)
-            c, cu, _, ns = t.probe(P, len(P), ksP, mode, timing_top=True)
-            dt, k = (t.build_ns + ns) * 1e-9, "reference"
-        else:
-            orc = pyoracle.Oracle()
-            t0 = time.perf_counter()
-            t = orc.build(kind, B, len(B), ksB, D)
-            t.probe_chaining(P, len(P), ksP, unique=(mode == 1), materialize=False)
-            dt, k = time.perf_counter() - t0, "port"
-        return {"value": (nR + nS) / dt, "unit": "tuples/s", "cores": 1, "kind": k, "host_cores": os.cpu_count(),
-                "sample": f"plan {args.plan}, build 2^{sb} / probe 2^{sb + (args.log2_probe - args.log2_build)}, 1 repetition, 1 thread "
-                          "(the reference is single-threaded)", "seconds": dt}
-    except Exception as e:  # the baseline is a reported side figure; never fail the bench for it
-        return {"value": None, "unit": "tuples/s", "cores": 1, "kind": "unavailable", "sample": repr(e)}
+def gen_relations(pkg, ctx, torch, dev, nR, nS, first_R, nRl, first_S, nSl, zipf):
+    """rows [first, first + n) of the two global relations (csrc/datagen.cu)"""
+    R = torch.zeros((nRl, 3), dtype=torch.int32, device=dev)
+    S = torch.zeros((nSl, 3), dtype=torch.int32, device=dev)
+    ctx.gen_column(R, 12, 0, first_R, nRl, pkg.capi.GEN_PERMUTATION, vmax=nR, seed=SEED_R)
+    ctx.gen_column(S, 12, 0, first_S, nSl, pkg.capi.GEN_IOTA)
+    if zipf > 0:
+        ctx.gen_column(S, 12, 4, first_S, nSl, pkg.capi.GEN_ZIPF, vmax=nR, zipf_q=zipf, seed=SEED_S)
+    else:
+        ctx.gen_column(S, 12, 4, first_S, nSl, pkg.capi.GEN_UNIFORM, vmax=nR, seed=SEED_S)
+    return R, S
+
+
+def torch_pair_checksum(torch, left, right):
+    """sum / xor of hj3d_pair_mix over (left, right) int64 tensors, independent of the engine (wrapping int64)"""
+    x = ((left << 32) | right) * (-7046029254386353131)        # 0x9E3779B97F4A7C15 as int64, wraps
+    x = x ^ ((x >> 32) & 0xFFFFFFFF)                           # logical shift
+    s = int(x.sum().item()) & M64
+    v = x.clone()
+    n = v.numel()
+    while n > 1:
+        h = n // 2
+        v[:h] ^= v[n - h:n]
+        n -= h
+    return s, (int(v[0].item()) & M64 if v.numel() else 0)
 
 
 def run_ours(args):
@@ -206,112 +252,124 @@ def run_ours(args):
     for o in args.opt:
         k, v = o.split("=")
         ctx.set_option(int(k), int(v))
+    lib = pkg.capi.load()
     kind_name, build_rel, mode = PLANS[args.plan]
     kind = pkg.CHAINING if kind_name == "chaining" else pkg.NESTED
     nR, nS = 1 << args.log2_build, 1 << args.log2_probe
-    # ---- synthetic relations, generated on the device (rank r holds rows [r*n/N, (r+1)*n/N) of both)
-    g = torch.Generator(device=dev); g.manual_seed(1234)
-    if world == 1:
-        Rk = torch.randperm(nR, device=dev, generator=g, dtype=torch.int64).to(torch.int32)
-    else:  # a bijection of [0, nR) that every rank can evaluate on its own slice: k -> (a*k + c) mod nR, a odd
-        lo = rank * (nR // world)
-        idx = torch.arange(lo, lo + nR // world, device=dev, dtype=torch.int64)
-        Rk = ((idx * 0x9E3779B1 + 12345) % nR).to(torch.int32)
     nRl, nSl = nR // world, nS // world
-    R = torch.zeros((nRl, 3), dtype=torch.int32, device=dev); R[:, 0] = Rk; del Rk
-    g.manual_seed(99 + rank)
-    S = torch.zeros((nSl, 3), dtype=torch.int32, device=dev)
-    S[:, 0] = torch.arange(rank * nSl, (rank + 1) * nSl, device=dev, dtype=torch.int64).to(torch.int32)
-    if args.zipf > 0:   # Zipf-like foreign keys (config 4): inverse-CDF of a continuous power law, rank r ~ u^(1/(1-s)); NOT the
-        # libstdc++ bit stream of the reference's generator (device-side generation is for scale runs, never for parity)
-        u = torch.rand(nSl, device=dev, generator=g, dtype=torch.float64)
-        if abs(args.zipf - 1.0) < 1e-9:
-            rk = torch.exp(u * float(__import__("math").log(nR)))
-        else:
-            a = 1.0 - args.zipf
-            rk = (u * (float(nR) ** a - 1.0) + 1.0) ** (1.0 / a)
-        S[:, 1] = (rk.to(torch.int64) - 1).clamp_(0, nR - 1).to(torch.int32)
-        del u, rk
-    else:
-        S[:, 1] = torch.randint(0, nR, (nSl,), device=dev, generator=g, dtype=torch.int64).to(torch.int32)
+    R, S = gen_relations(pkg, ctx, torch, dev, nR, nS, rank * nRl, nRl, rank * nSl, nSl, args.zipf)
     ksRk, ksSa = pkg.KeySpec(12, 0), pkg.KeySpec(12, 4)
     B, ksB, nBl, P, ksP, nPl = (R, ksRk, nRl, S, ksSa, nSl) if build_rel == "R" else (S, ksSa, nSl, R, ksRk, nRl)
     nBg, nPg = (nR, nS) if build_rel == "R" else (nS, nR)
+
+    def all_sum(vals):
+        if dist is None:
+            return [int(v) for v in vals]
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in vals], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        return [int(x) & M64 for x in t.tolist()]
+
+    def all_xor(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        x = 0
+        for o in out:
+            x ^= int(o.item()) & M64
+        return x
+
+    # numDvSa = #distinct S.a over the GLOBAL relation (the directory size of build-on-S plans, main_experiment1.cc:875)
     if build_rel == "R":
         D = nR
     else:
-        D = nR - int(nR * (1 - 1 / nR) ** nS) if nR > 1 else 1     # ~ #distinct S.a (numDvSa); any D is a valid table size
-        if args.zipf > 0:
-            D = max(int(torch.unique(S[:, 1]).numel()), 1)             # numDvSa of the skewed column (N=1 only)
-    ks_rec = pkg.KeySpec(8, 0, 4, 0, 4)
-    lib = pkg.capi.load()
-    if world > 1:
-        lo_, hi_ = C.c_uint64(), C.c_uint64()
-        lib.hj3d_owner_range(D, world, rank, C.byref(lo_), C.byref(hi_))
-        table = ctx.table(kind, D, shard=(lo_.value, hi_.value))
-    else:
-        table = ctx.table(kind, D)
-    cap_out = int(nS // world * 1.25) + 1024 if world > 1 else nS
-    out = torch.empty((cap_out, 2), dtype=torch.int32, device=dev)
-    nest = torch.empty((max(nPl * (2 if world > 1 else 1), 1), 2), dtype=torch.int32, device=dev) if mode == 3 else None
-    part_B = torch.empty((nBl, 2), dtype=torch.int32, device=dev) if world > 1 else None
-    part_P = torch.empty((nPl, 2), dtype=torch.int32, device=dev) if world > 1 else None
+        present = torch.zeros(nR, dtype=torch.uint8, device=dev)
+        present[S[:, 1].to(torch.int64)] = 1
+        if dist is not None:
+            dist.all_reduce(present, op=dist.ReduceOp.MAX)
+        D = max(int(present.sum(dtype=torch.int64).item()), 1)
+        del present
+    # ---- expected result checksum, computed in plain torch from the generated data (every N)
+    def expected_checksum():
+        Rk = torch.zeros((nR, 1), dtype=torch.int32, device=dev)
+        ctx.gen_column(Rk, 4, 0, 0, nR, pkg.capi.GEN_PERMUTATION, vmax=nR, seed=SEED_R)     # the whole key column of R
+        inv = torch.empty(nR, dtype=torch.int64, device=dev)
+        inv[Rk[:, 0].to(torch.int64)] = torch.arange(nR, dtype=torch.int64, device=dev)
+        del Rk
+        s_tot, x_tot, cnt = 0, 0, 0
+        step_ = 1 << 26
+        for lo in range(0, nSl, step_):
+            hi = min(nSl, lo + step_)
+            srow = torch.arange(rank * nSl + lo, rank * nSl + hi, dtype=torch.int64, device=dev)
+            rrow = inv[S[lo:hi, 1].to(torch.int64)]
+            left, right = (srow, rrow) if build_rel == "R" else (rrow, srow)    # result pair = (probe row, build row)
+            s, x = torch_pair_checksum(torch, left, right)
+            s_tot = (s_tot + s) & M64; x_tot ^= x; cnt += hi - lo
+        del inv
+        torch.cuda.empty_cache()
+        s_tot, cnt = all_sum([s_tot, cnt])
+        return s_tot, all_xor(x_tot), cnt
+
+    exp_sum, exp_xor, exp_cnt = expected_checksum()
+    assert exp_cnt == nS
     flags = pkg.F_CHECKSUM if args.checksum else 0
     state = {}
+    cap_out = int(nS // world * 1.25) + 4096 if world > 1 else nS
+    if args.zipf > 0 and world > 1:
+        cap_out = nS                                            # a hot key's owner may produce most of the result
+    out = torch.empty((cap_out, 2), dtype=torch.int32, device=dev)
 
-    def expected_checksum_sum():
-        """Independent full-size check in plain torch: for a key/foreign-key join the result multiset is
-        {(i, inv[S.a[i]])}; fold hj3d_pair_mix over it with wrapping int64 arithmetic (N=1, build on R)."""
-        inv = torch.empty(nR, dtype=torch.int64, device=dev)
-        inv[R[:, 0].to(torch.int64)] = torch.arange(nR, dtype=torch.int64, device=dev)
-        total = 0
-        step_ = 1 << 26
-        for lo in range(0, nS, step_):
-            hi = min(nS, lo + step_)
-            left = torch.arange(lo, hi, dtype=torch.int64, device=dev)
-            right = inv[S[lo:hi, 1].to(torch.int64)]
-            x = ((left << 32) | right) * (-7046029254386353131)        # 0x9E3779B97F4A7C15 as int64, wraps
-            x = x ^ ((x >> 32) & 0xFFFFFFFF)                           # logical shift
-            total = (total + int(x.sum().item())) & ((1 << 64) - 1)
-        return total
+    comm = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pkg.Comm.unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        comm = pkg.Comm.create(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
+        slack = 1.25 if args.zipf <= 0 else float(world)        # skew: one owner may receive most of a relation
+        comm.reserve(0, int(nBg / world * slack) + (1 << 20), 4)
+        comm.reserve(1, int(nPg / world * slack) + (1 << 20), 4)
+        lo_, hi_ = comm.shard(D)
+        table = ctx.table(kind, D, shard=(lo_, hi_))
+    else:
+        table = ctx.table(kind, D)
+    xflags = pkg.capi.XCHG_EXACT if (args.zipf > 0 or args.exact_exchange) else 0
 
-    recv_B = torch.empty((int(nBl * 1.3) + 4096, 2), dtype=torch.int32, device=dev) if world > 1 else None
-    recv_P = torch.empty((int(nPl * 1.3) + 4096, 2), dtype=torch.int32, device=dev) if world > 1 else None
-
-    def exchange_both():
-        """owner partition of both relations, one collective for all counts, one all-to-all-v per relation"""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        cB = ctx.partition_by_owner(B, nBl, ksB, D, world, rank * nBl, part_B)
-        cP = ctx.partition_by_owner(P, nPl, ksP, D, world, rank * nPl, part_P)
-        ev[1].record()
-        (rb, _), (rp, _) = pkg.sharding.exchange_many(dist, [part_B, part_P], [cB, cP], dev, [recv_B, recv_P])
-        ev[2].record()
-        state["xev"] = ev
-        state["shuffle_bytes"] = 8 * (nBl - cB[rank]) + 8 * (nPl - cP[rank])
-        return rb, rb.shape[0], rp, rp.shape[0]
-
-    def step():
-        state["shuffle_bytes"] = 0
+    def step(fl=None):
+        fl = flags if fl is None else fl
         table.clear()
         if world > 1:
-            bsrc, nb, psrc, npb = exchange_both()
-            kb, kp = ks_rec, ks_rec
-        else:
-            bsrc, nb, psrc, npb, kb, kp = B, nBl, P, nPl, ksB, ksP
-        table.build(bsrc, nb, kb)
-        tb = ctx.timings()
-        if mode <= 1:
-            rc, c = table.probe_chaining(psrc, npb, kp, unique=(mode == 1), flags=flags, out=out, out_cap=cap_out)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            comm.begin(0, B, nBl, ksB, D, rank * nBl, xflags)
+            comm.begin(1, P, nPl, ksP, D, rank * nPl, xflags)
+            rc0, pb = comm.end(0, B, rank * nBl, nBg)
+            rc1, pp = comm.end(1, P, rank * nPl, nPg)
+            ev[1].record()
+            assert rc0 == 0 and rc1 == 0, "exchange region overflow (run with --exact-exchange)"
+            table.build_parts(pb)
+            tb = ctx.timings()
+            rc, c, u = table.probe_parts(pp, mode, flags=fl, out=out, out_cap=cap_out)
             tp = ctx.timings()
-            res = c
+            ev[2].record()
+            res = u if mode == 3 else c
+            state.update(xev=ev, sent=8 * (pb.info()["n_sent_remote"] + pp.info()["n_sent_remote"]), n_probe_local=pp.info()["n_records"],
+                         n_build_local=pb.info()["n_records"])
+            pb.destroy(); pp.destroy()
         else:
-            # AlgNestJoinProbe directly followed by AlgUnnestHt (plans Nsr / Nrs): one fused call
-            rc, c, res = table.probe_nested_unnest(psrc, npb, kp, flags=flags, out=out, out_cap=cap_out)
+            table.build(B, nBl, ksB)
+            tb = ctx.timings()
+            if mode <= 1:
+                rc, c = table.probe_chaining(P, nPl, ksP, unique=(mode == 1), flags=fl, out=out, out_cap=cap_out)
+                res = c
+            else:
+                # AlgNestJoinProbe directly followed by AlgUnnestHt (plans Nsr / Nrs): one fused call
+                rc, c, res = table.probe_nested_unnest(P, nPl, ksP, flags=fl, out=out, out_cap=cap_out)
             tp = ctx.timings()
-            state["unnest_ms"] = 0.0
+            state.update(n_probe_local=nPl, n_build_local=nBl)
         assert rc == 0, "result buffer overflow"
-        state.update(build=tb, probe=tp, probe_counters=c, result=res, n_probe_local=npb)
+        state.update(build=tb, probe=tp, probe_counters=c, result=res)
         return res
 
     def sync_all():
@@ -320,13 +378,52 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    verified = None
-    if world == 1 and build_rel == "R":
-        flags_keep, flags = flags, pkg.F_CHECKSUM
-        res0 = step()                                                  # untimed verification run with the checksum on
-        flags = flags_keep
-        verified = bool(res0["checksum_sum"] == expected_checksum_sum() and res0["out_tuples"] == nS)
-        assert verified, "full-size result checksum differs from the independent torch computation"
+    # ---- verification (untimed, checksum on): every N
+    res0 = step(pkg.F_CHECKSUM)
+    pc0 = dict(state["probe_counters"])
+    got_sum, got_cnt, got_cmps, got_match = all_sum([res0["checksum_sum"], res0["out_tuples"], pc0["num_cmps"], pc0["matches"]])
+    got_xor = all_xor(res0["checksum_xor"])
+    verified = bool((got_sum, got_xor, got_cnt) == (exp_sum, exp_xor, nS))
+    assert verified, f"result checksum / count differ from the independent torch computation: {(got_sum, got_xor, got_cnt)} vs {(exp_sum, exp_xor, nS)}"
+    # merged HtStatistics of the shards
+    my_stats = table.stats()
+    if dist is not None:
+        names = list(my_stats)
+        t = torch.tensor([my_stats[k] - (1 << 64) if my_stats[k] >= (1 << 63) else my_stats[k] for k in names], dtype=torch.int64, device=dev)
+        allst = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allst, t)
+        parts = (pkg.Stats * world)(*[pkg.Stats(**{k: int(v) & M64 for k, v in zip(names, a.tolist())}) for a in allst])
+        merged = pkg.Stats()
+        lib.hj3d_stats_merge(parts, world, C.byref(merged))
+        merged_stats = merged.as_dict()
+    else:
+        merged_stats = my_stats
+    verified_unsharded = None
+    if world > 1 and not args.no_unsharded_check:
+        # rank 0 joins the SAME global relations on its own, through the single-GPU path, and all ranks' merged counters
+        # must equal what it gets: count, numCmps, out_tuples, every HtStatistics field
+        ok = 1
+        if rank == 0:
+            Rg, Sg = gen_relations(pkg, ctx, torch, dev, nR, nS, 0, nR, 0, nS, args.zipf)
+            Bg, Pg = (Rg, Sg) if build_rel == "R" else (Sg, Rg)
+            tg = ctx.table(kind, D).build(Bg, nBg, ksB)
+            if mode <= 1:
+                _, cg = tg.probe_chaining(Pg, nPg, ksP, unique=(mode == 1), flags=pkg.F_CHECKSUM)
+                ug = cg
+            else:
+                _, cg, ug = tg.probe_nested_unnest(Pg, nPg, ksP, flags=pkg.F_CHECKSUM)
+            one = (cg["matches"], cg["num_cmps"], ug["out_tuples"], ug["checksum_sum"], ug["checksum_xor"], tg.stats())
+            many = (got_match, got_cmps, got_cnt, got_sum, got_xor, merged_stats)
+            ok = int(one == many)
+            if not ok:
+                print(f"[bench] sharded result differs from the unsharded engine path: {many} vs {one}", file=sys.stderr)
+            tg.destroy(); del Rg, Sg, Bg, Pg
+            torch.cuda.empty_cache()
+        t = torch.tensor([ok], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        verified_unsharded = bool(t.item())
+        assert verified_unsharded, "sharded join differs from the unsharded engine path on the same data"
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -335,7 +432,7 @@ def run_ours(args):
     sync_all()
     launches0 = ctx.timings()["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    probe_ms, build_ms = [], []
+    probe_ms, build_ms, l1_ms, xchg_ms, join_ms = [], [], [], [], []
     sync_all()
     if sampler:
         sampler.t_begin = time.perf_counter()
@@ -343,6 +440,7 @@ def run_ours(args):
     for _ in range(args.steps):
         res = step()
         probe_ms.append(state["probe"]["probe_ms"]); build_ms.append(state["build"]["total_ms"])
+        l1_ms.append(state["probe"]["partition_l1_ms"])
     e1.record()
     sync_all()
     if sampler:
@@ -354,49 +452,62 @@ def run_ours(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        tot = torch.tensor([res["out_tuples"], state["probe_counters"]["num_cmps"], launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(tot)
-        out_total, cmps_total, launches = [int(x) for x in tot.tolist()]
-    else:
-        out_total, cmps_total = res["out_tuples"], state["probe_counters"]["num_cmps"]
-    # size-independent correctness properties at full size: every S tuple finds exactly one R partner
+    out_total, cmps_total, launches = all_sum([res["out_tuples"], state["probe_counters"]["num_cmps"], launches])
     assert out_total == nS, f"join produced {out_total} tuples, expected |S| = {nS}"
+    assert cmps_total == got_cmps
     value = (nR + nS) / (ms * 1e-3)
-    # ---- the other table variant on the same relations (N=1, default plan only): nested 3D table + deferred unnest
+    peak, peak_src = peaks()
+
+    # ---- the other plans on the same relations (N=1, default plan only): the nested 3D table, and both tables built on the
+    #      NON-unique side S (the paper's subject: plans Crs / Nrs)
     other = None
     if world == 1 and args.plan == "Csr" and not args.no_other_plans:
-        try:
-            t2 = ctx.table(pkg.NESTED, D)
-            def step_nsr():
-                t2.clear()
-                t2.build(B, nBl, ksB)
-                b_ms = ctx.timings()["total_ms"]
-                rc_, c_, r_ = t2.probe_nested_unnest(P, nPl, ksP, flags=0, out=out, out_cap=cap_out)
-                return r_, b_ms, ctx.timings()["total_ms"], 0.0
-            for _ in range(2):
-                step_nsr()
-            torch.cuda.synchronize(); a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(3):
-                r_, b_ms, p_ms, u_ms = step_nsr()
-            a1.record(); torch.cuda.synchronize()
-            ms2 = a0.elapsed_time(a1) / 3
-            assert r_["out_tuples"] == nS
-            other = {"Nsr": {"ms_per_step": ms2, "value": (nR + nS) / (ms2 * 1e-3), "unit": "tuples/s", "steps": 3, "warmup": 2,
-                             "build_ms": b_ms, "probe_call_ms": p_ms, "unnest_ms": u_ms,
-                             "join_frac": algorithmic_bytes(nBg, nPg, nS, nS, D, nested=True) / (ms2 * 1e-3) / 1e9 / peaks()[0],
-                             "note": "nested 3D table + nested probe + unnest (plan Nsr) on the same relations; the unnest directly follows "
-                                     "the probe in this plan, so both run as one fused call (hj3d_probe_nested_unnest)"}}
-            t2.destroy()
-        except Exception as ex:
-            other = {"Nsr": {"error": repr(ex)}}
+        other = {}
+        for oplan in ("Nsr", "Crs", "Nrs"):
+            try:
+                okind, obuild, omode = PLANS[oplan]
+                oB, oksB, onB, oP, oksP, onP = (R, ksRk, nR, S, ksSa, nS) if obuild == "R" else (S, ksSa, nS, R, ksRk, nR)
+                if obuild == "R":
+                    oD = nR
+                else:
+                    present = torch.zeros(nR, dtype=torch.uint8, device=dev); present[S[:, 1].to(torch.int64)] = 1
+                    oD = max(int(present.sum(dtype=torch.int64).item()), 1); del present
+                t2 = ctx.table(pkg.CHAINING if okind == "chaining" else pkg.NESTED, oD)
+
+                def ostep():
+                    t2.clear()
+                    t2.build(oB, onB, oksB)
+                    b_ms = ctx.timings()["total_ms"]
+                    if omode == 3:
+                        _, c_, r_ = t2.probe_nested_unnest(oP, onP, oksP, flags=0, out=out, out_cap=cap_out)
+                    else:
+                        _, c_ = t2.probe_chaining(oP, onP, oksP, unique=False, flags=0, out=out, out_cap=cap_out); r_ = c_
+                    return r_, b_ms, ctx.timings()["total_ms"]
+                for _ in range(2):
+                    ostep()
+                torch.cuda.synchronize(); a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(3):
+                    r_, b_ms, p_ms = ostep()
+                a1.record(); torch.cuda.synchronize()
+                ms2 = a0.elapsed_time(a1) / 3
+                assert r_["out_tuples"] == nS
+                nBo, nPo = (nR, nS) if obuild == "R" else (nS, nR)
+                other[oplan] = {"ms_per_step": ms2, "value": (nR + nS) / (ms2 * 1e-3), "unit": "tuples/s", "steps": 3, "warmup": 2,
+                                "build_ms": b_ms, "probe_call_ms": p_ms, "num_buckets": oD,
+                                "join_frac": algorithmic_bytes(nBo, nPo, min(nPo, nS) if omode == 3 else 0, nS, oD, nested=(omode == 3)) / (ms2 * 1e-3) / 1e9 / peak}
+                t2.destroy()
+            except Exception as ex:
+                other[oplan] = {"error": repr(ex)}
+        other["note"] = ("same relations; Nsr: nested 3D table on R + fused nested probe / unnest; Crs / Nrs: chaining / nested table built "
+                         "on the NON-unique side S (2^30 rows, ~8 duplicates per key), probed with R")
+
     # ---- e2e: host buffers through hj3d_join_host (H2D of both relations + D2H of the counters inside)
     e2e = None
     if world == 1 and not args.no_e2e:
         try:
             hB = torch.empty((nBl, 3), dtype=torch.int32).pin_memory(); hB.copy_(B)
             hP = torch.empty((nPl, 3), dtype=torch.int32).pin_memory(); hP.copy_(P)
-            out_keep = out
             del out
             torch.cuda.empty_cache()
             ts = []
@@ -410,68 +521,84 @@ def run_ours(args):
             e2e_s = sum(ts) / len(ts)
             e2e = {"value": (nR + nS) / e2e_s, "unit": "tuples/s", "h2d_bytes_per_step": 12 * (nR + nS),
                    "d2h_bytes_per_step": 56, "ms_per_step": e2e_s * 1e3, "steps": len(ts),
-                   "note": "pinned host relations -> hj3d_join_host -> counters on the host; result pairs materialised in HBM"}
+                   "h2d_gbs_if_the_copy_were_everything": 12 * (nR + nS) / e2e_s / 1e9,
+                   "note": "pinned host relations -> hj3d_join_host -> counters on the host.  The reference's result is a COUNT "
+                           "(AlgTop, algebra.hh:223-229): the 2^30 result pairs are materialised in HBM and stay there, only the "
+                           "counters (56 B) come back; the step is bound by the 14.5 GB host-to-device copy"}
             del hB, hP
         except Exception as ex:
             e2e = {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 12 * (nR + nS), "d2h_bytes_per_step": 56,
                    "error": repr(ex)}
     if rank != 0:
+        if comm is not None:
+            sync_all(); comm.destroy()
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak, peak_src = peaks()
     nested = mode == 3
-    nested_plan = nested
-    nM = state["probe_counters"]["matches"] if nested else 0
-    alg = algorithmic_bytes(nBg, nPg, nM * world if nested else 0, nS, D, nested=nested)
-    # dominant kernel of the step (largest share in profiles/*launches*): the shared-memory probe kernel.  Bytes that ONE
-    # launch must move: per probe tuple the 8-byte (key, id) record it reads and the 8-byte result pair it writes, plus
-    # the table slices it stages once (4-byte directory word per bucket + 8-byte slot / 16-byte group per build row).
-    # (The 12-byte row-store tuples are read by the partition pass, not by this kernel; join_frac below charges the
-    # whole join, partition passes included, against SURVEY 8(d)'s algorithmic bytes.)
+    nM = got_match if nested else 0
+    alg = algorithmic_bytes(nBg, nPg, nM, nS, D, nested=nested)
+    # ---- roofline of the DOMINANT kernel of the step (largest share in profiles/*launches*): the level-1 partition pass of the
+    # probe side, k_part_scatter (at N > 1 the same kernel with peer stores: the exchange).  Its algorithmic bytes: the
+    # 12-byte row-store tuple it reads + the 8-byte (key, id) record it writes, per probe tuple of this GPU.
+    l1 = sum(l1_ms) / len(l1_ms) if l1_ms and world == 1 else None
     pm = sum(probe_ms) / len(probe_ms)
-    n_res = res["out_tuples"] if not nested_plan else state["probe_counters"]["matches"]
-    table_bytes = 4 * (D // world) + (nBg // world) * 8 if not nested_plan else 4 * (D // world) + 16 * min(nBg, D) // world
-    probe_bytes = state["n_probe_local"] * 8 + n_res * 8 + table_bytes
-    kernel_name = {1: "k_probe_fine<chaining, IsBuildKeyUnique>", 0: "k_probe_chaining_smem", 3: "k_probe_fine<nested>"}[mode]
-    traffic = None                                   # from the committed ncu capture of this kernel at this configuration, if any
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel_name)
-        if tj and (tj["plan"], tj["log2_build"], tj["log2_probe"], tj["n_gpus"]) == (args.plan, args.log2_build, args.log2_probe, world) \
-                and args.zipf <= 0:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+            "join_algorithmic_bytes": alg, "join_frac": alg / (ms * 1e-3) / 1e9 / peak / world}
+    if world == 1:
+        l1_bytes = nPl * 20
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_part_scatter_level1")
+            if tj and (tj["plan"], tj["log2_build"], tj["log2_probe"], tj["n_gpus"]) == (args.plan, args.log2_build, args.log2_probe, 1) and args.zipf <= 0:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roof.update({"kernel": "k_part_scatter (probe side, level 1: 12-byte row-store tuples -> (key, id) records of coarse bucket ranges)",
+                     "achieved": l1_bytes / (l1 * 1e-3) / 1e9 if l1 else None, "frac": l1_bytes / (l1 * 1e-3) / 1e9 / peak if l1 else None,
+                     "kernel_ms": l1, "algorithmic_bytes_per_launch": l1_bytes, "traffic": traffic,
+                     "note": "frac is this kernel's own bytes over its own CUDA-event time; join_frac charges the WHOLE step (all partition "
+                             "passes, build, probe) against SURVEY 8(d)'s 37.58 GB and is the headline fraction",
+                     "probe_kernel": {"kernel": "k_probe_fine" if mode == 1 else "probe", "kernel_ms": pm,
+                                      "algorithmic_bytes_per_launch": nPl * 16 + 4 * D + 8 * nBg,
+                                      "frac": (nPl * 16 + 4 * D + 8 * nBg) / (pm * 1e-3) / 1e9 / peak if pm else None}})
+    else:
+        part_ms = state["xev"][0].elapsed_time(state["xev"][1])
+        roof.update({"kernel": "k_part_scatter<PEER> (exchange = partition level 1 with peer stores)", "kernel_ms": part_ms, "traffic": None,
+                     "achieved": (nBl + nPl) * 20 / (part_ms * 1e-3) / 1e9, "frac": (nBl + nPl) * 20 / (part_ms * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_launch": (nBl + nPl) * 20,
+                     "note": "both relations' exchange kernels + count all-gathers (rank 0, last step); NVLink, not HBM, bounds it: see shuffle"})
     line = {"metric": "join input tuples/sec (build+probe)", "value": value, "unit": "tuples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic (device generated, identical at every N)",
             "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e if e2e is not None else {"value": None, "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                                "note": "e2e is measured at N=1"},
-            "roofline": {"bound": "hbm", "kernel": kernel_name,
-                         "achieved": probe_bytes / (pm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": probe_bytes / (pm * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel_ms": pm, "algorithmic_bytes_per_launch": probe_bytes,
-                         "join_algorithmic_bytes": alg, "join_frac": alg / (ms * 1e-3) / 1e9 / peak / world},
+            "roofline": roof,
             "phases_ms": {"build_total": sum(build_ms) / len(build_ms), "histogram": state["build"]["histogram_ms"],
                           "scan": state["build"]["scan_ms"], "scatter": state["build"]["scatter_ms"],
                           "group": state["build"]["group_ms"], "build_partition": state["build"]["partition_ms"],
-                          "probe_partition": state["probe"]["partition_ms"], "probe": pm, "unnest": state.get("unnest_ms", 0.0)},
-            "result": {"out_tuples": out_total, "num_cmps": cmps_total, "verified_checksum": verified,
+                          "probe_partition": state["probe"]["partition_ms"], "probe_partition_level1": l1, "probe": pm},
+            "result": {"out_tuples": out_total, "num_cmps": cmps_total, "num_buckets": D, "verified_checksum": verified,
+                       "verified_vs_unsharded_engine": verified_unsharded, "ht_statistics": merged_stats,
                        "checksum_in_timed_steps": bool(args.checksum)}}
     if world > 1:
         part_ms = state["xev"][0].elapsed_time(state["xev"][1])
-        a2a_ms = state["xev"][1].elapsed_time(state["xev"][2])
-        line["shuffle"] = {"bytes_sent_per_gpu": state["shuffle_bytes"], "partition_by_owner_ms": part_ms, "all_to_all_ms": a2a_ms,
-                           "bus_gbs_per_gpu": state["shuffle_bytes"] / (a2a_ms * 1e-3) / 1e9 if a2a_ms > 0 else None,
-                           "note": "rank 0, last step: owner partition of both relations, then one counts collective + one NCCL "
-                                   "all_to_all_single of (key,row id) records per relation; against ~770 GB/s measured peer bandwidth "
-                                   "per direction"}
+        join_ms_ = state["xev"][1].elapsed_time(state["xev"][2])
+        line["shuffle"] = {"bytes_sent_per_gpu": state["sent"], "exchange_ms": part_ms, "local_join_ms": join_ms_,
+                           "bus_gbs_per_gpu": state["sent"] / (part_ms * 1e-3) / 1e9 if part_ms > 0 else None,
+                           "exact_two_pass": bool(xflags),
+                           "note": "rank 0, last step.  exchange_ms = partition level 1 of both relations with peer stores into the owners' "
+                                   "receive buffers + two count all-gathers (the only collectives); there is no separate all-to-all.  "
+                                   "bus_gbs_per_gpu = bytes this GPU stored into other GPUs / exchange_ms (a lower bound on the link rate, "
+                                   "the kernel also hashes and ranks); measured peer copy bandwidth is ~770 GB/s per direction"}
     if other is not None:
         line["other_plans"] = other
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(args)
+        line["cpu_baseline"] = cpu_baseline_leg(args, pkg, ctx)
     print(json.dumps(line), flush=True)
+    if comm is not None:
+        sync_all(); comm.destroy()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -489,7 +616,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the nested plan (N=1)")
+    ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the other plans (N=1)")
+    ap.add_argument("--no-unsharded-check", action="store_true", help="N>1: skip rank 0's unsharded join of the same data")
+    ap.add_argument("--exact-exchange", action="store_true", help="N>1: two-pass exchange with exact regions (always on with --zipf)")
     ap.add_argument("--zipf", type=float, default=0.0, help="skew of the foreign keys S.a (0 = uniform; config 4 uses 0.5 .. 1.5)")
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")

@@ -117,6 +117,8 @@ typedef struct {
 typedef struct {
   float partition_ms, histogram_ms, scan_ms, scatter_ms, group_ms, probe_ms, unnest_ms, total_ms;
   uint64_t kernel_launches; /* kernels launched by the engine since ctx creation */
+  float partition_l1_ms;    /* the level-1 k_part_scatter launch alone (first one of the call) */
+  float reserved_;
 } hj3d_timings;
 
 typedef struct hj3d_ctx   hj3d_ctx;
@@ -144,6 +146,24 @@ int hj3d_memcpy_h2d(hj3d_ctx* ctx, void* d_dst, const void* h_src, uint64_t byte
 int hj3d_memcpy_d2h(hj3d_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes);
 /* d_dst[i] = first + i  (identity column, e.g. the `left` of a second deferred unnest) */
 int hj3d_iota_u32(hj3d_ctx* ctx, uint32_t* d_dst, uint64_t n, uint32_t first);
+
+/* ---- device-side input generation for scale runs (csrc/datagen.cu) --------------------------------------------------
+ * Fills the uint32 attribute at `offset` of n row-store tuples (tuple_bytes wide) for global rows first_row .. first_row+n:
+ *   HJ3D_GEN_IOTA         value = row id                                  (S.k, main_experiment1.cc:438-441)
+ *   HJ3D_GEN_PERMUTATION  a bijection of [0, vmax) applied to the row id  (R.k = std::shuffle(iota), main_experiment1.cc:430-436)
+ *   HJ3D_GEN_UNIFORM      uniform on [0, vmax)                            (GenRandIntVec::generate_uni, util/GenRandIntVec.cc:71-98)
+ *   HJ3D_GEN_ZIPF         (Zipf(vmax, q) - 1 + shift) % vmax by rejection-inversion (util/zipf_distribution.hh:48-58,
+ *                         GenRandIntVec.cc:290-293)
+ *   HJ3D_GEN_CONST        value = shift
+ * The reference's distributions, NOT its libstdc++ bit stream (parity runs use the reference's own generator).  Every value
+ * is a pure function of (seed, row id), so any rank of a multi-GPU run generates any slice of one global relation. */
+#define HJ3D_GEN_IOTA 0
+#define HJ3D_GEN_PERMUTATION 1
+#define HJ3D_GEN_UNIFORM 2
+#define HJ3D_GEN_ZIPF 3
+#define HJ3D_GEN_CONST 4
+int hj3d_gen_column_u32(hj3d_ctx* ctx, void* d_tuples, uint32_t tuple_bytes, uint32_t offset, uint64_t first_row, uint64_t n,
+                        int kind, uint64_t vmax, double zipf_q, uint64_t shift, uint64_t seed);
 
 /* ---- build side ----------------------------------------------------------------------------
  * hj3d_table_create  <- HtChaining1 / HtNested1 constructors via AlgHashJoinBuild(aHashDirSize, ..)

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header(pkg):
     assert C.sizeof(pkg.KeySpec) == 20
     assert C.sizeof(pkg.Counters) == 7 * 8
     assert C.sizeof(pkg.Stats) == 19 * 8
-    assert C.sizeof(pkg.Timings) == 8 * 4 + 8
+    assert C.sizeof(pkg.Timings) == 8 * 4 + 8 + 2 * 4
 
 
 def test_pair_mix_agrees_with_oracle(pkg, oracle):
