@@ -327,6 +327,8 @@ def run_ours(args):
             idt = torch.frombuffer(bytearray(pkg.Comm.unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(idt, 0)
         comm = pkg.Comm.create(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
+        if args.xranges:
+            comm.set_option(pkg.capi.XOPT_TARGET_RANGES, args.xranges)
         slack = 1.25 if args.zipf <= 0 else float(world)        # skew: one owner may receive most of a relation
         comm.reserve(0, int(nBg / world * slack) + (1 << 20), 4)
         comm.reserve(1, int(nPg / world * slack) + (1 << 20), 4)
@@ -619,6 +621,7 @@ def main():
     ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the other plans (N=1)")
     ap.add_argument("--no-unsharded-check", action="store_true", help="N>1: skip rank 0's unsharded join of the same data")
     ap.add_argument("--exact-exchange", action="store_true", help="N>1: two-pass exchange with exact regions (always on with --zipf)")
+    ap.add_argument("--xranges", type=int, default=0, help="N>1: coarse bucket ranges of the exchange (default: the engine's 256)")
     ap.add_argument("--zipf", type=float, default=0.0, help="skew of the foreign keys S.a (0 = uniform; config 4 uses 0.5 .. 1.5)")
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")

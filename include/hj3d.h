@@ -274,7 +274,7 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
  * flags: HJ3D_XCHG_EXACT = two passes (histogram first, regions packed at exact offsets): for skewed keys whose ranges
  *        overflow the uniform regions (hj3d_exchange_end returns HJ3D_OVERFLOW then; nothing is lost by retrying). */
 #define HJ3D_XCHG_EXACT 1u
-#define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256) */
+#define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256; 128 with more than one rank) */
 #define HJ3D_XOPT_MIN_RANGE_WIDTH 2 /* smallest range width in buckets (default 16384: a multiple of every fine-partition width) */
 typedef struct hj3d_comm  hj3d_comm;
 typedef struct hj3d_parts hj3d_parts;
