@@ -468,26 +468,29 @@ int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done, const Par
   const uint32_t hdr_bytes = (2 * (Wf + 1) * 4 + 15) & ~15u;
   uint32_t cap_recs = kNfThreads * kNfItems;
   const uint32_t smem_max = 160u << 10;
-  if (hdr_bytes + (uint64_t)cap_recs * (sizeof(Slot<KeyT>) + 1) > smem_max) cap_recs = (smem_max - hdr_bytes) / (sizeof(Slot<KeyT>) + 1);
+  constexpr uint32_t kPerRec = nf_bytes_per_record<KeyT>();                  // record + group word + group start + bucket
+  if (hdr_bytes + (uint64_t)cap_recs * kPerRec > smem_max) cap_recs = (smem_max - hdr_bytes) / kPerRec;
   const uint64_t expect = n / F + n / (2ull * F) + 512;                      // expected records per range + 50% + 512
   if (expect < cap_recs) cap_recs = (uint32_t)expect;
   cap_recs &= ~15u;
-  const size_t sm = hdr_bytes + (size_t)cap_recs * (sizeof(Slot<KeyT>) + 1);  // records + one leader flag byte each
+  const size_t sm = hdr_bytes + (size_t)cap_recs * kPerRec;
   Group<KeyT>* gtmp = nullptr;                                             // one slot per build row: #groups is only known afterwards
-  unsigned long long* lookback = nullptr;
+  unsigned long long *gcount = nullptr, *gbase = nullptr;
   HJ_TRY(dev_alloc(c, &gtmp, n));
-  HJ_TRY(dev_alloc(c, &lookback, (uint64_t)F));
+  HJ_TRY(dev_alloc(c, &gcount, (uint64_t)F + 1));
+  HJ_TRY(dev_alloc(c, &gbase, (uint64_t)F + 1));
   HJ_TRY(buf_ensure(c, t->b_goff, &t->goff, (uint64_t)nl + 1));
   HJ_TRY(buf_ensure(c, t->b_rows, &t->rows, n));
-  CUDA_TRY(cudaMemsetAsync(lookback, 0, (size_t)F * 8, c->stream));
   uint32_t* d_flag = (uint32_t*)(c->d_scalar + 2);
   CUDA_TRY(cudaMemsetAsync(c->d_scalar, 0, 4 * sizeof(unsigned long long), c->stream));
   HJ_TRY(init_dev_stats_copies(c));
   CUDA_TRY(cudaFuncSetAttribute(k_build_fine_nested<HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   k_build_fine_nested<HASH><<<F, kNfThreads, sm, c->stream>>>(fine.recs, fine.part_start, fine.counts, base, t->dir, Wf, F, cap_recs,
-                                                              t->goff, gtmp, t->rows, lookback, c->d_stats, d_flag, c->d_scalar);
+                                                              t->goff, gtmp, t->rows, gcount, c->d_stats, d_flag);
   k_stats_fold<<<1, 32, 0, c->stream>>>(c->d_stats, kStatsCopies);
   c->launches += 2;
+  // first global group index of every partition; the total goes to the host (the groups array is sized from it)
+  HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{gcount}, StoreExU64{gbase}, F, (DevStats*)nullptr, c->d_scalar)));
   unsigned long long* h = (unsigned long long*)c->h_pinned;
   CUDA_TRY(cudaMemcpyAsync(h, c->d_scalar, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -496,7 +499,9 @@ int build_nested_fine(hj3d_ctx* c, hj3d_table* t, Src src, bool* done, const Par
   const uint64_t G = h[0];
   Group<KeyT>* groups = nullptr;
   HJ_TRY(buf_ensure(c, t->b_groups, &groups, G));
-  if (G) CUDA_TRY(cudaMemcpyAsync(groups, gtmp, G * sizeof(Group<KeyT>), cudaMemcpyDeviceToDevice, c->stream));
+  k_nested_compact<KeyT><<<F, 256, 0, c->stream>>>(gtmp, base, gbase, gcount, Wf, nl, F, groups, t->goff);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
   t->groups = groups; t->n_groups = G; t->n = fine.n_kept; t->slots = nullptr;
   t->parts = 1; t->part_width = nl ? nl : 1;
   CUDA_TRY(cudaMemcpyAsync(&t->hstats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));

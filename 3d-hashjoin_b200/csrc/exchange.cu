@@ -86,6 +86,7 @@ struct hj3d_comm {
   unsigned long long* d_cursor[kSlots] = {nullptr, nullptr};   // [kMaxRanges] my counts per range
   unsigned long long* d_all[kSlots] = {nullptr, nullptr};      // [world][kMaxRanges] everybody's counts
   unsigned long long* d_pstart[kSlots] = {nullptr, nullptr};   // [kMaxRanges + 1] my region offsets inside the owners' buffers
+  unsigned long long* d_bar = nullptr;                         // [1 + kMaxPeers] barrier scratch (exact mode)
   cudaEvent_t ev_scatter[kSlots] = {nullptr, nullptr};
   ExchangePlan plan[kSlots];
   uint64_t cap_seg[kSlots] = {0, 0};
@@ -209,6 +210,8 @@ int comm_alloc_state(hj3d_comm* cm) {
     CUDA_TRY(cudaMalloc((void**)&cm->d_pstart[s], (kMaxRanges + 1) * 8));
     CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_scatter[s], cudaEventDisableTiming));
   }
+  CUDA_TRY(cudaMalloc((void**)&cm->d_bar, (1 + kMaxPeers) * 8));
+  CUDA_TRY(cudaMemset(cm->d_bar, 0, (1 + kMaxPeers) * 8));
   CUDA_TRY(cudaMallocHost(&cm->h_pinned, (size_t)(cm->world + 1) * kMaxRanges * 8));
   return HJ3D_OK;
 }
@@ -292,6 +295,7 @@ int hj3d_comm_destroy(hj3d_comm* cm) {
     cudaFree(cm->d_cursor[s]); cudaFree(cm->d_all[s]); cudaFree(cm->d_pstart[s]);
     if (cm->ev_scatter[s]) cudaEventDestroy(cm->ev_scatter[s]);
   }
+  cudaFree(cm->d_bar);
   if (cm->h_pinned) cudaFreeHost(cm->h_pinned);
   if (cm->nc) nccl().CommDestroy(cm->nc);
   if (cm->group) { auto& r = cm->group->ranks; for (auto& p : r) if (p == cm) p = nullptr; }
@@ -442,8 +446,7 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
       return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_EXACT needs one process per rank (or a group of one): the second pass is a collective");
     HJ_TRY(exact_second_pass(cm, slot, d_tuples, rowid_base, h_all));
     // barrier: everybody's second pass is done before anybody reads (the gathered cursors are not needed)
-    unsigned long long* scratch = cm->d_all[slot] + (size_t)cm->world * kMaxRanges - cm->world;   // tail of d_all is free: world <= 16
-    if (cm->nc) NCCL_TRY(nccl().AllGather(cm->d_cursor[slot], scratch, 1, ncclUint64, cm->nc, c->stream));
+    if (cm->nc) NCCL_TRY(nccl().AllGather(cm->d_bar, cm->d_bar + 1, 1, ncclUint64, cm->nc, c->stream));
   }
   const uint32_t n_owned = pl.owned(cm->rank), n_seg = n_owned * cm->world;
   auto parts = std::make_unique<hj3d_parts>();

@@ -219,6 +219,7 @@ struct Experiment1 {
 }  // namespace
 
 int main(int argc, char** argv) {
+  hj3d::Runtime::instance().cache_uploads(true);   // the relations do not change between the repetitions of a plan
   long R = -1, S = -1, t = -1, b = 1; int skew = -1; std::string file; std::vector<std::string> plans = {"all"};
   bool printRelations = false;
   auto need = [&](int& i) -> std::string { if (i + 1 >= argc) usage("missing value"); return argv[++i]; };

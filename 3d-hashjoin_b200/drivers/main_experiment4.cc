@@ -176,6 +176,7 @@ struct Experiment4 {
 }  // namespace
 
 int main(int argc, char** argv) {
+  hj3d::Runtime::instance().cache_uploads(true);   // the relations do not change between the repetitions of a plan
   long R = -1, a = -1, b = -1, A = -1, B = -1; std::string file; std::vector<std::string> plans = {"all"};
   for (int i = 1; i < argc; ++i) {
     std::string k = argv[i];

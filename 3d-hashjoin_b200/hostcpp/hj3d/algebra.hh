@@ -84,7 +84,14 @@ class AlgBase {
     inline uint64_t runs() const { return _runs; }
     inline duration_t getRuntime() const { return std::chrono::duration_cast<duration_t>(_stopTime - _startTime); }
     inline std::string getRuntimeStr() const { return std::to_string(getRuntime().count()) + " ns"; }
+    // Device operators do their work in one batch when their strand ends, so the reference's inclusive wall-clock
+    // timers (init .. fin) and their differences (get_runtime_excl, algebra.hh:129-138) say nothing about them.  They
+    // record the CUDA-event time of their own kernels instead (hj3d_ctx_timings); that IS an exclusive runtime.
+    inline void       setDeviceTime(double ms) { _deviceNs = (int64_t)(ms * 1e6); }
+    inline bool       hasDeviceTime() const { return _deviceNs >= 0; }
+    inline duration_t deviceTime() const { return duration_t(_deviceNs < 0 ? 0 : _deviceNs); }
   protected:
+    int64_t      _deviceNs = -1;
     uint64_t     _count;
     bool         _ok;
     time_point_t _startTime, _stopTime;
@@ -94,8 +101,11 @@ class AlgBase {
 
 template <alg_operator_c Toperator>
 auto get_runtime_excl(const Toperator* aOp) -> typename Toperator::duration_t {   // algebra.hh:129-138
-  if constexpr (requires(Toperator t) { t.consumer(); }) return (aOp->getRuntime() - aOp->consumer()->getRuntime());
-  else return aOp->getRuntime();
+  if (aOp->hasDeviceTime()) return aOp->deviceTime();                    // device operator: its kernels' CUDA-event time
+  if constexpr (requires(Toperator t) { t.consumer(); }) {
+    if (aOp->consumer()->hasDeviceTime()) return typename Toperator::duration_t(0);   // host hand-over stage in front of a device operator
+    return (aOp->getRuntime() - aOp->consumer()->getRuntime());
+  } else return aOp->getRuntime();
 }
 template <alg_operator_c Toperator>
 void print_strand(const Toperator* aOp, const size_t aIndentLvl = 0, std::ostream& os = std::cout) {   // algebra.hh:148-162
@@ -105,6 +115,13 @@ void print_strand(const Toperator* aOp, const size_t aIndentLvl = 0, std::ostrea
 }
 
 namespace hj3d::detail {
+struct DevClock { double ms = 0; inline void tick(); };
+inline double last_call_device_ms() {
+  hj3d_timings t{};
+  check(hj3d_ctx_timings(Runtime::instance().ctx(), &t));
+  return t.total_ms;
+}
+inline void DevClock::tick() { ms += last_call_device_ms(); }
 // bulk / device hand-over hooks an operator may offer to its producer
 template <class C, class In> concept takes_bulk = requires(C c, In* p, size_t n, typename C::globstat_t* g) { c.step_bulk(p, n, g); };
 template <class C> concept counts_only = requires(C c, uint64_t n) { { c.wants_tuples() } -> std::same_as<bool>; c.add_count(n); };
@@ -209,7 +226,10 @@ class BuildOp : public AlgBase {
     inline void init([[maybe_unused]] globstat_t* g) { reset(); }
     inline void step(input_t* aInput, [[maybe_unused]] globstat_t* g) { inc(); _hashtable.insert(aInput); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { inc(n); _hashtable.insert_bulk(first, n); }
-    inline void fin([[maybe_unused]] globstat_t* g) { _hashtable.seal(); stopTimer(); }   // the device build happens here
+    inline void fin([[maybe_unused]] globstat_t* g) {                                     // the device build happens here
+      if (_hashtable.seal()) setDeviceTime(hj3d::detail::last_call_device_ms());
+      stopTimer();
+    }
     inline const hashtable_t& hashtable() const { return _hashtable; }
     inline void clear_ht() { _hashtable.clear(); }
   protected:
@@ -292,7 +312,7 @@ class AlgUnnestHt : public AlgBase {
     static_assert(std::is_same_v<output_t, typename unnestfun_t::output_t>,
                   "AlgUnnestHt::output_t (aka consumer_t::input_t) does not match unnestfun_t::output_t");
     inline AlgUnnestHt(consumer_t* aConsumer) : AlgBase("AlgUnnest"), _consumer(aConsumer), _outputTuple() {}
-    inline void init([[maybe_unused]] globstat_t* g) { reset(); _consumer->init(g); _in.clear(); _dev = {nullptr, nullptr, 0}; _table = nullptr; }
+    inline void init([[maybe_unused]] globstat_t* g) { reset(); _clk.ms = 0; _consumer->init(g); _in.clear(); _dev = {nullptr, nullptr, 0}; _table = nullptr; }
     inline void step(input_t* aNestedTuple, [[maybe_unused]] globstat_t* g) { _in.push_back(*aNestedTuple); }
     // device hand-over from AlgNestJoinProbe: (left id, group_ref) columns + how to rebuild a nested tuple
     using make_nested_t = std::function<std::remove_const_t<input_t>(uint32_t)>;
@@ -326,10 +346,11 @@ class AlgUnnestHt : public AlgBase {
         run_device(table, dl, dg, n, make_nested_t([this](uint32_t i) { return _in[i]; }), g);
       }
       _consumer->fin(g);
-      stopTimer();
+      setDeviceTime(_clk.ms); stopTimer();
     }
     inline const consumer_t* consumer() const { return _consumer; }
   private:
+    hj3d::detail::DevClock _clk;
     void run_device(const ht_nested_t* table, const uint32_t* d_left, const uint32_t* d_gref, uint64_t n, const make_nested_t& make, globstat_t* g) {
       using namespace hj3d;
       hj3d_ctx* c = Runtime::instance().ctx();
@@ -337,15 +358,15 @@ class AlgUnnestHt : public AlgBase {
       bool need_tuples = true;
       if constexpr (detail::counts_only<consumer_t>) need_tuples = _consumer->wants_tuples();
       if (!need_tuples) {
-        check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, nullptr, 0, &cnt));
+        check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, nullptr, 0, &cnt)); _clk.tick();
         inc(cnt.out_tuples);
         if constexpr (detail::counts_only<consumer_t>) _consumer->add_count(cnt.out_tuples);
         return;
       }
-      check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, nullptr, 0, &cnt));           // size of the result
+      check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, nullptr, 0, &cnt)); _clk.tick();           // size of the result
       const uint64_t m = cnt.out_tuples;
       auto* dout = (uint32_t*)_dout.ensure(m * 8 + 8);
-      check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, dout, m, &cnt));
+      check(hj3d_unnest(c, table->handle(), d_left, d_gref, n, 0, dout, m, &cnt)); _clk.tick();
       std::vector<uint32_t> pairs(2 * m);
       check(hj3d_memcpy_d2h(c, pairs.data(), dout, m * 8));
       // emission order of the reference (algebra.hh:526-539): nested tuples in input order; inside a group the
@@ -392,7 +413,7 @@ class AlgNestJoinProbe : public AlgBase {
       : AlgBase("AlgNestJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {
       hj3d::check_key_equality_predicate<joinpred_t, hashfun_t, typename build_t::hashfun_t>("AlgNestJoinProbe: Tjoinpred");
     }
-    inline void init(globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
+    inline void init(globstat_t* g) { reset(); _clk.ms = 0; _numCmps = 0; _in.clear(); _consumer->init(g); }
     inline void step(input_t* aProbeTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aProbeTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
     inline void fin(globstat_t* g) {
@@ -405,21 +426,21 @@ class AlgNestJoinProbe : public AlgBase {
       bool need_tuples = true;
       if constexpr (detail::counts_only<consumer_t>) need_tuples = _consumer->wants_tuples();
       if (!need_tuples) {
-        check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, nullptr, 0, &cnt));
+        check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, nullptr, 0, &cnt)); _clk.tick();
         if constexpr (detail::counts_only<consumer_t>) _consumer->add_count(cnt.matches);
       } else {
         if constexpr (detail::is_device_unnest<consumer_t>::value) {
           if (!_consumer->needs_host_tuples()) {                     // probe -> unnest -> count: one fused device call
             hj3d_counters ucnt{};
-            check(hj3d_probe_nested_unnest(c, table.handle(), dprobe, n, _in.ks, 0, nullptr, 0, &cnt, &ucnt));
+            check(hj3d_probe_nested_unnest(c, table.handle(), dprobe, n, _in.ks, 0, nullptr, 0, &cnt, &ucnt)); _clk.tick();
             _consumer->take_fused_count(ucnt.out_tuples);
             inc(cnt.matches); _numCmps += cnt.num_cmps;
-            _consumer->fin(g); stopTimer();
+            _consumer->fin(g); setDeviceTime(_clk.ms); stopTimer();
             return;
           }
         }
         auto* dout = (uint32_t*)_dout.ensure(n * 8 + 8);
-        check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, dout, n, &cnt));
+        check(hj3d_probe_nested(c, table.handle(), dprobe, n, _in.ks, nullptr, 0, dout, n, &cnt)); _clk.tick();
         const uint64_t m = cnt.out_written;
         auto* dl = (uint32_t*)_dl.ensure(m * 4 + 4); auto* dg = (uint32_t*)_dg.ensure(m * 4 + 4);
         check(hj3d_split_pairs(c, dout, m, dl, dg));
@@ -429,7 +450,7 @@ class AlgNestJoinProbe : public AlgBase {
           if constexpr (detail::is_device_unnest<consumer_t>::value)
             _consumer->step_device(detail::NestedBatch{dl, dg, m}, &table, typename consumer_t::make_nested_t(), g);
           inc(cnt.matches); _numCmps += cnt.num_cmps;
-          _consumer->fin(g); stopTimer();
+          _consumer->fin(g); setDeviceTime(_clk.ms); stopTimer();
           return;
         }
         auto* dfirst = (uint32_t*)_dfirst.ensure(m * 4 + 4);
@@ -455,11 +476,12 @@ class AlgNestJoinProbe : public AlgBase {
       inc(cnt.matches);
       _numCmps += cnt.num_cmps;
       _consumer->fin(g);
-      stopTimer();
+      setDeviceTime(_clk.ms); stopTimer();
     }
     inline const consumer_t* consumer() const { return _consumer; }
     inline uint64_t numCmps() const { return _numCmps; }
   private:
+    hj3d::detail::DevClock _clk;
     consumer_t* _consumer;
     build_t*    _buildOperator;
     output_t    _outputTuple;
@@ -482,7 +504,7 @@ class AlgHashJoinProbe : public AlgBase {
       : AlgBase("AlgHashJoinProbe"), _consumer(aConsumer), _buildOperator(aBuildOperator), _outputTuple(), _numCmps() {
       hj3d::check_key_equality_predicate<joinpred_t, hashfun_t, typename build_t::hashfun_t>("AlgHashJoinProbe: Tjoinpred");
     }
-    inline void init([[maybe_unused]] globstat_t* g) { reset(); _numCmps = 0; _in.clear(); _consumer->init(g); }
+    inline void init([[maybe_unused]] globstat_t* g) { reset(); _clk.ms = 0; _numCmps = 0; _in.clear(); _consumer->init(g); }
     inline void step(input_t* aTuple, [[maybe_unused]] globstat_t* g) { _in.push_copy(aTuple); }
     inline void step_bulk(input_t* first, size_t n, [[maybe_unused]] globstat_t* g) { _in.seq.push_bulk(first, n); }
     inline void fin(globstat_t* g) {
@@ -494,13 +516,13 @@ class AlgHashJoinProbe : public AlgBase {
       hj3d_counters cnt{};
       bool need_tuples = true;
       if constexpr (detail::counts_only<consumer_t>) need_tuples = _consumer->wants_tuples();
-      check(hj3d_probe_chaining(c, table.handle(), dprobe, n, _in.ks, nullptr, IsBuildKeyUnique ? 1 : 0, 0, nullptr, 0, &cnt));
+      check(hj3d_probe_chaining(c, table.handle(), dprobe, n, _in.ks, nullptr, IsBuildKeyUnique ? 1 : 0, 0, nullptr, 0, &cnt)); _clk.tick();
       if (!need_tuples) {
         if constexpr (detail::counts_only<consumer_t>) _consumer->add_count(cnt.matches);
       } else {
         const uint64_t m = cnt.out_tuples;
         auto* dout = (uint32_t*)_dout.ensure(m * 8 + 8);
-        check(hj3d_probe_chaining(c, table.handle(), dprobe, n, _in.ks, nullptr, IsBuildKeyUnique ? 1 : 0, 0, dout, m, &cnt));
+        check(hj3d_probe_chaining(c, table.handle(), dprobe, n, _in.ks, nullptr, IsBuildKeyUnique ? 1 : 0, 0, dout, m, &cnt)); _clk.tick();
         std::vector<uint32_t> pairs(2 * m);
         check(hj3d_memcpy_d2h(c, pairs.data(), dout, m * 8));
         // probe order like the tuple-at-a-time reference; within one probe tuple the reference emits its matches in
@@ -533,11 +555,12 @@ class AlgHashJoinProbe : public AlgBase {
       inc(cnt.matches);
       _numCmps += cnt.num_cmps;
       _consumer->fin(g);
-      stopTimer();
+      setDeviceTime(_clk.ms); stopTimer();
     }
     inline const consumer_t* consumer() const { return _consumer; }
     inline uint64_t numCmps() const { return _numCmps; }
   private:
+    hj3d::detail::DevClock _clk;
     consumer_t* _consumer;
     build_t*    _buildOperator;
     output_t    _outputTuple;

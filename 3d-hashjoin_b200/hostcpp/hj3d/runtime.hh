@@ -31,11 +31,14 @@ class Runtime {
       return _ctx;
     }
     void device(int d) { _device = d; }
+    void cache_uploads(bool on) { _cache = on; }
+    bool cache_uploads() const { return _cache; }
     ~Runtime() { if (_ctx) hj3d_ctx_destroy(_ctx); }
   private:
     Runtime() = default;
     hj3d_ctx* _ctx = nullptr;
     int       _device = 0;
+    bool      _cache = false;
 };
 
 // grow-only device buffer
@@ -53,9 +56,10 @@ class DevBuf {
       }
       return _p;
     }
-    void release() { if (_p) { hj3d_mem_free(Runtime::instance().ctx(), _p); _p = nullptr; _cap = 0; } }
+    void release() { if (_p) { hj3d_mem_free(Runtime::instance().ctx(), _p); _p = nullptr; _cap = 0; } tag_ptr = nullptr; tag_n = 0; }
     void* get() const { return _p; }
     template <class T> T* as() const { return static_cast<T*>(_p); }
+    const void* tag_ptr = nullptr; uint64_t tag_n = 0;          // what the buffer holds a copy of (upload cache)
   private:
     void*    _p = nullptr;
     uint64_t _cap = 0;
@@ -121,8 +125,9 @@ template <class Tpred, class HashL, class HashR>
 void check_key_equality_predicate(const char* what) {
   using left_t = std::remove_const_t<typename Tpred::left_t>;
   using right_t = std::remove_const_t<typename Tpred::right_t>;
-  if constexpr (has_explicit_keyspec<HashL> || has_explicit_keyspec<HashR>) {
-    return;
+  if constexpr (has_explicit_keyspec<HashL> || has_explicit_keyspec<HashR> || requires { typename HashL::hj3d_base; } ||
+                requires { typename HashR::hj3d_base; }) {
+    return;   // the functor reaches its key through a pointer: random tuples cannot be synthesised (its base functor is checked)
   } else if constexpr (!std::is_same_v<left_t, std::remove_const_t<typename HashL::input_t>> ||
                        !std::is_same_v<right_t, std::remove_const_t<typename HashR::input_t>> ||
                        !std::is_trivially_copyable_v<left_t> || !std::is_trivially_copyable_v<right_t>) {

@@ -605,6 +605,114 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ config 3: main_experiment4
+def run_config3(args):
+    """BASELINE config 3: the deferred-unnesting join of main_experiment4 (plan Ndu: nested tables on S and T, scan R ->
+    probe S -> probe T -> unnest T -> unnest S -> count, main_experiment4.cc:831-941) with duplicates per key
+    A = B in {1, 10, 100, 1000} on one GPU, as one device pipeline (hj3d_probe2_unnest2); plan Chj (two chaining joins,
+    main_experiment4.cc:943-1043) composed from the single-operator calls beside it; the unmodified reference
+    (oracle/_ref) timed on the same arrays where that takes seconds."""
+    import numpy as np
+    import torch
+    import hj3d_loader
+    pkg = hj3d_loader.load()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ctx = pkg.Context(0, stream=torch.cuda.current_stream().cuda_stream)
+    ref = pyoracle.Ref() if pyoracle.Ref.available() else None
+    points = [(24, 4, 3, 1, 1), (24, 4, 3, 10, 10), (20, 4, 3, 100, 100), (14, 4, 3, 1000, 1000), (22, 4, 3, 100, 1), (22, 4, 3, 1, 100)]
+    if args.c3_points:
+        points = [tuple(int(x) for x in q.split(",")) for q in args.c3_points]
+    ks_k, ks_a = pkg.KeySpec(8, 0), pkg.KeySpec(8, 4)
+    rows = []
+    for (r, alpha, beta, A, Bm) in points:
+        nR = 1 << r
+        nC, nE = nR >> alpha, nR >> beta
+        cC, cE = nC * A, nE * Bm
+        nF = cC + cE
+        D = nC + nE                                                   # numFkCommon + numFkExclusive buckets (main_experiment4.cc:855)
+        R = torch.zeros((nR, 2), dtype=torch.int32, device=dev)
+        ctx.gen_column(R, 8, 0, 0, nR, pkg.capi.GEN_IOTA)
+
+        def fk_relation(seed, excl_base):
+            """generateFkRel (main_experiment4.cc:740-756): shuffled common keys first, then the shuffled exclusive ones"""
+            F = torch.zeros((nF, 2), dtype=torch.int32, device=dev)
+            ctx.gen_column(F, 8, 0, 0, nF, pkg.capi.GEN_IOTA)
+            pc = torch.zeros((cC, 1), dtype=torch.int32, device=dev)
+            ctx.gen_column(pc, 4, 0, 0, cC, pkg.capi.GEN_PERMUTATION, vmax=cC, seed=seed)
+            F[:cC, 1] = (pc[:, 0].to(torch.int64) // A).to(torch.int32)
+            pe = torch.zeros((cE, 1), dtype=torch.int32, device=dev)
+            ctx.gen_column(pe, 4, 0, 0, cE, pkg.capi.GEN_PERMUTATION, vmax=cE, seed=seed + 1)
+            F[cC:, 1] = (excl_base + pe[:, 0].to(torch.int64) // Bm).to(torch.int32)
+            return F
+        S = fk_relation(11, nC)
+        T = fk_relation(23, nC + nE)
+        c_top = nC * A * A
+        tS, tT = ctx.table(pkg.NESTED, D), ctx.table(pkg.NESTED, D)
+        materialise = c_top * 12 <= (16 << 30)
+        trip = torch.empty((max(c_top, 1), 3), dtype=torch.int32, device=dev) if materialise else None
+
+        def step_ndu(flags=0):
+            tS.clear(); tT.clear()
+            tS.build(S, nF, ks_a); bS = ctx.timings()["total_ms"]
+            tT.build(T, nF, ks_a); bT = ctx.timings()["total_ms"]
+            rc, cnt, _, _ = ctx.probe2_unnest2(tS, tT, R, nR, ks_k, flags=flags, out=trip, out_cap=c_top if materialise else 0)
+            return cnt, bS, bT, ctx.timings()["total_ms"]
+        cnt, _, _, _ = step_ndu(pkg.F_CHECKSUM)
+        assert (cnt[0]["matches"], cnt[1]["matches"], cnt[2]["out_tuples"], cnt[3]["out_tuples"]) == (nC + nE, nC, nC * A, c_top), cnt
+        chk = (cnt[3]["checksum_sum"], cnt[3]["checksum_xor"])
+        step_ndu()
+        torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            cnt, bS, bT, pr = step_ndu()
+        e1.record(); torch.cuda.synchronize()
+        ms_ndu = e0.elapsed_time(e1) / 3
+        tS.destroy(); tT.destroy()
+        # plan Chj: chaining tables, probe S (|S| results, materialised), probe T through the gathered R tuples
+        cS, cT = ctx.table(pkg.CHAINING, D), ctx.table(pkg.CHAINING, D)
+        p1 = torch.empty((nF, 2), dtype=torch.int32, device=dev)
+        p2 = torch.empty((max(c_top, 1), 2), dtype=torch.int32, device=dev) if c_top * 8 <= (16 << 30) else None
+
+        def step_chj():
+            cS.clear(); cT.clear()
+            cS.build(S, nF, ks_a); cT.build(T, nF, ks_a)
+            _, c1 = cS.probe_chaining(R, nR, ks_k, flags=0, out=p1, out_cap=nF)
+            r1 = p1[:c1["out_written"], 0].contiguous()
+            _, c2 = cT.probe_chaining(R, c1["out_written"], ks_k, gather=r1, flags=0, out=p2, out_cap=c_top if p2 is not None else 0)
+            return c1, c2
+        c1, c2 = step_chj()
+        assert (c1["out_tuples"], c2["out_tuples"]) == (nF, c_top), (c1, c2)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(3):
+            step_chj()
+        e1.record(); torch.cuda.synchronize()
+        ms_chj = e0.elapsed_time(e1) / 3
+        cS.destroy(); cT.destroy()
+        row = {"log2R": r, "alpha": alpha, "beta": beta, "A": A, "B": Bm, "cardR": nR, "cardS": nF, "cardT": nF, "c_top": c_top,
+               "Ndu_ms": ms_ndu, "Ndu_build_S_ms": bS, "Ndu_build_T_ms": bT, "Ndu_probe_pipeline_ms": pr,
+               "Ndu_input_tuples_per_s": (nR + 2 * nF) / (ms_ndu * 1e-3), "Ndu_results_per_s": c_top / (ms_ndu * 1e-3),
+               "results_materialised": bool(materialise), "Chj_ms": ms_chj,
+               "counters": {"c_probe_RS": cnt[0]["matches"], "c_probe_RS_cmp": cnt[0]["num_cmps"], "c_probe_RT": cnt[1]["matches"],
+                            "c_probe_RT_cmp": cnt[1]["num_cmps"], "c_unnest1": cnt[2]["out_tuples"], "c_top": cnt[3]["out_tuples"]}}
+        if ref is not None and c_top <= (1 << 27) and nF <= (1 << 26):
+            hR, hS, hT = (x.cpu().numpy().view(np.uint32) for x in (R, S, T))
+            w0 = ref.exp4_run(0, hR, hS, hT, D); w1 = ref.exp4_run(1, hR, hS, hT, D)
+            row["cpu_reference"] = {"Ndu_ms": (w0["t_build_S_ns"] + w0["t_build_T_ns"] + w0["t_probe_ns"]) * 1e-6,
+                                    "Chj_ms": (w1["t_build_S_ns"] + w1["t_build_T_ns"] + w1["t_probe_ns"]) * 1e-6, "cores": 1,
+                                    "same_arrays": True,
+                                    "counters_equal": bool(all(w0[k] == row["counters"][k] for k in row["counters"]) and
+                                                           (w0["checksum_sum"], w0["checksum_xor"]) == chk)}
+            assert row["cpu_reference"]["counters_equal"], (w0, row["counters"], chk)
+        rows.append(row)
+        del R, S, T, trip, p1, p2
+        torch.cuda.empty_cache()
+    print(json.dumps({"metric": "config 3: main_experiment4 deferred-unnesting join (plans Ndu / Chj), duplicates per key 1..1000, one B200",
+                      "unit": "ms per step (build S + build T + probe strand)", "n_gpus": 1, "steps": 3, "warmup": 2, "points": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -626,7 +734,11 @@ def main():
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (HJ3D_OPT_*), repeatable")
+    ap.add_argument("--config", type=int, default=2, help="2 = the headline KFK join (default); 3 = main_experiment4 duplicate sweep (N=1)")
+    ap.add_argument("--c3-points", action="append", default=[], help="config 3 point log2R,alpha,beta,A,B (repeatable)")
     args = ap.parse_args()
+    if args.config == 3:
+        return run_config3(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <sstream>
 #include <functional>
 #include <iostream>
 #include <memory>
@@ -119,11 +120,19 @@ template <class L, class R> struct FlatIds {
 struct RefTable {
   virtual ~RefTable() {}
   virtual void stats(orc_stats*) const = 0;
+  virtual std::string stats_text() const = 0;
   virtual int  kind() const = 0;
   virtual uint32_t tuple_bytes() const = 0;
   virtual uint32_t key_offset() const = 0;
   virtual int  hash_id() const = 0;
 };
+
+static std::string stats_text_of(const HtStatistics& hs) {
+  std::ostringstream os;
+  hs.print(os);
+  os << '\x1e' << hs.toCsvString() << '\x1e' << HtStatistics::toCsvStringHeader();
+  return os.str();
+}
 
 static void fill_stats(const HtStatistics& hs, orc_stats* s) {
   s->num_buckets = hs._numBuckets; s->num_empty = hs._numEmptyBuckets;
@@ -149,6 +158,7 @@ struct ChainingTable : RefTable {
     if (n) std::memcpy((void*)rel._tuples.data(), tuples, n * BB);
   }
   void run_build() { GlobStat gs; AlgScan<build_t> scan(&op, &rel); scan.run(&gs); }
+  std::string stats_text() const override { return stats_text_of(op.hashtable().makeStatistics()); }
   void stats(orc_stats* s) const override {
     std::memset(s, 0, sizeof(*s));
     fill_stats(op.hashtable().makeStatistics(), s);
@@ -176,6 +186,7 @@ struct NestedTable : RefTable {
     if (n) std::memcpy((void*)rel._tuples.data(), tuples, n * BB);
   }
   void run_build() { GlobStat gs; AlgScan<build_t> scan(&op, &rel); scan.run(&gs); }
+  std::string stats_text() const override { return stats_text_of(op.hashtable().makeStatistics()); }
   void stats(orc_stats* s) const override {
     std::memset(s, 0, sizeof(*s));
     fill_stats(op.hashtable().makeStatistics(), s);
@@ -370,6 +381,13 @@ void* ref_build(int kind, const void* tuples, uint64_t n, orc_keyspec ks, uint64
 void ref_free(void* h) { delete (RefTable*)h; }
 
 void ref_stats(void* h, orc_stats* s) { ((RefTable*)h)->stats(s); }
+
+/* the reference's own HtStatistics::print / toCsvString / toCsvStringHeader bytes (ht_statistics.cc:16-79), '\x1e' separated */
+uint64_t ref_stats_text(void* h, char* buf, uint64_t cap) {
+  const std::string s = ((RefTable*)h)->stats_text();
+  if (buf && cap) { const uint64_t n = s.size() < cap - 1 ? s.size() : cap - 1; std::memcpy(buf, s.data(), n); buf[n] = 0; }
+  return s.size();
+}
 
 /* mode: 0 chaining, 1 chaining IsBuildKeyUnique, 2 nested (no unnest), 3 nested + unnest.
  * timing_top != 0: use the drivers' AlgTop sink (no checksum / materialisation) and report the
