@@ -130,8 +130,16 @@ k_group_claim(const Slot<typename HashT<HASH>::key_t>* __restrict__ slots, uint6
       if (++p == len) p = 0;
     }
     rep[i] = c;
-    atomicAdd(gcnt + c, 1u);
-    atomicMin(gmin + c, me.rowid);
+    // Skewed keys: millions of rows of one key update the same two words.  Slots are bucket ordered, so a hot key fills whole
+    // warps: lanes that share a cell combine their update (one atomic pair per warp instead of 32 serialised ones).
+    const uint32_t peers = __match_any_sync(__activemask(), c);
+    if (__popc(peers) == 1) {
+      atomicAdd(gcnt + c, 1u);
+      atomicMin(gmin + c, me.rowid);
+    } else {
+      const uint32_t mn = __reduce_min_sync(peers, me.rowid);
+      if ((uint32_t)__ffs(peers) - 1u == lane_id()) { atomicAdd(gcnt + c, (uint32_t)__popc(peers)); atomicMin(gmin + c, mn); }
+    }
   }
 }
 

@@ -909,10 +909,16 @@ int probe_nested_unnest_impl(hj3d_ctx* c, hj3d_table* t, Src src, uint32_t flags
   const size_t sm = pl.fc.smem_bytes;
   const Slot<KeyT>* recs = (const Slot<KeyT>*)pl.src.base;
   const Group<KeyT>* groups = (const Group<KeyT>*)t->groups;
+  // probe records that hit a group of more than kUnnestWarpMax rows are listed and expanded by finish_fused_unnest
+  const uint32_t hot_cap = (uint32_t)(c->unnest_hot_cap > 0 ? c->unnest_hot_cap : 1);
+  HotGroup* hot_list = nullptr;
+  HJ_TRY(dev_alloc(c, &hot_list, hot_cap));
+  CUDA_TRY(cudaMemsetAsync(c->d_scalar + 1, 0, 8, c->stream));
+  c->fused_hot_list = hot_list; c->fused_hot_cap = hot_cap;
 #define LAUNCH_PU(C, W) do { \
     CUDA_TRY(cudaFuncSetAttribute(k_probe_nested_unnest<HASH, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
     k_probe_nested_unnest<HASH, C, W><<<pl.n_work, kFineThreads, sm, c->stream>>>(recs, t->dir, pl.fc, pl.work, pl.work_part, t->goff, groups, \
-                                                                                   t->rows, out, cap, c->d_ctr); } while (0)
+                                                                                   t->rows, out, cap, c->d_ctr, hot_list, hot_cap, c->d_scalar + 1); } while (0)
   if (cs) { if (wr) LAUNCH_PU(true, true); else LAUNCH_PU(true, false); }
   else    { if (wr) LAUNCH_PU(false, true); else LAUNCH_PU(false, false); }
 #undef LAUNCH_PU
@@ -969,6 +975,39 @@ int unnest_impl(hj3d_ctx* c, hj3d_table* t, const uint32_t* left, const uint32_t
   return HJ3D_OK;
 }
 
+
+// After the fused nested probe + unnest kernel: expand the listed hot groups, fetch the counters.  *redo = true: the hot list
+// overflowed (more than HJ3D_OPT_UNNEST_HOT_CAP hot probe hits): the caller runs the two-operator composition instead.
+int finish_fused_unnest(hj3d_ctx* c, hj3d_table* t, uint32_t flags, uint2* out, uint64_t cap, hj3d_counters* probe_out,
+                        hj3d_counters* unnest_out, bool* redo) {
+  *redo = false;
+  unsigned long long* h_hot = (unsigned long long*)((char*)c->h_pinned + 512);
+  CUDA_TRY(cudaMemcpyAsync(h_hot, c->d_scalar + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const unsigned long long n_hot = *h_hot;
+  if (n_hot > c->fused_hot_cap) { *redo = true; return HJ3D_OK; }
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  if (n_hot && (cs || wr)) {
+    PhaseTimer pt(c, PH_UNNEST);
+    const dim3 grid((unsigned)(n_hot < 1024 ? n_hot : 1024), kHotSplit);
+    const HotGroup* hl = (const HotGroup*)c->fused_hot_list;
+    if (cs) { if (wr) k_unnest_hot_groups<true, true><<<grid, 256, 0, c->stream>>>(hl, (uint32_t)n_hot, t->rows, out, cap, c->d_ctr);
+              else    k_unnest_hot_groups<true, false><<<grid, 256, 0, c->stream>>>(hl, (uint32_t)n_hot, t->rows, out, cap, c->d_ctr); }
+    else      k_unnest_hot_groups<false, true><<<grid, 256, 0, c->stream>>>(hl, (uint32_t)n_hot, t->rows, out, cap, c->d_ctr);
+    ++c->launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  DevCounters* h = (DevCounters*)c->h_pinned;
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaGetLastError());
+  probe_out->matches = h->matches; probe_out->num_cmps = h->num_cmps; probe_out->out_tuples = h->matches;
+  unnest_out->matches = h->out_cursor; unnest_out->out_tuples = h->out_cursor;
+  unnest_out->checksum_sum = h->checksum_sum; unnest_out->checksum_xor = h->checksum_xor;
+  unnest_out->overflow = (wr && h->out_cursor > cap) ? 1 : 0;
+  unnest_out->out_written = wr ? (h->out_cursor > cap ? cap : h->out_cursor) : 0;
+  return HJ3D_OK;
+}
 
 int table_matches(hj3d_table* t, const hj3d_keyspec& ks) {
   if (!t->built) return fail(HJ3D_ERR_INVALID, "table has not been built");
@@ -1402,17 +1441,11 @@ int hj3d_probe_nested_unnest(hj3d_ctx* c, hj3d_table* t, const void* d_probe, ui
   end_call(c);
   if (rc < 0) return rc;
   if (fused) {
-    DevCounters* h = (DevCounters*)c->h_pinned;
-    CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaGetLastError());
-    probe_out->matches = h->matches; probe_out->num_cmps = h->num_cmps; probe_out->out_tuples = h->matches;
-    unnest_out->matches = h->out_cursor; unnest_out->out_tuples = h->out_cursor;
-    unnest_out->checksum_sum = h->checksum_sum; unnest_out->checksum_xor = h->checksum_xor;
-    const bool wr = d_out != nullptr;
-    unnest_out->overflow = (wr && h->out_cursor > cap) ? 1 : 0;
-    unnest_out->out_written = wr ? (h->out_cursor > cap ? cap : h->out_cursor) : 0;
-    return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+    bool redo = false;
+    HJ_TRY(finish_fused_unnest(c, t, flags, (uint2*)d_out, cap, probe_out, unnest_out, &redo));
+    end_call(c);
+    if (!redo) return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+    memset(probe_out, 0, sizeof(*probe_out)); memset(unnest_out, 0, sizeof(*unnest_out));
   }
   // composition: nested tuples into a ctx-owned buffer, then the unnest of the pairs
   auto& hj = c->hj;
@@ -1501,17 +1534,11 @@ int hj3d_probe_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32
     return probe_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
   }
   if (fused) {
-    DevCounters* h = (DevCounters*)c->h_pinned;
-    CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaGetLastError());
-    probe_out->matches = h->matches; probe_out->num_cmps = h->num_cmps; probe_out->out_tuples = h->matches;
-    unnest_out->matches = h->out_cursor; unnest_out->out_tuples = h->out_cursor;
-    unnest_out->checksum_sum = h->checksum_sum; unnest_out->checksum_xor = h->checksum_xor;
-    const bool wr = d_out != nullptr;
-    unnest_out->overflow = (wr && h->out_cursor > cap) ? 1 : 0;
-    unnest_out->out_written = wr ? (h->out_cursor > cap ? cap : h->out_cursor) : 0;
-    return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+    bool redo = false;
+    HJ_TRY(finish_fused_unnest(c, t, flags, (uint2*)d_out, cap, probe_out, unnest_out, &redo));
+    end_call(c);
+    if (!redo) return unnest_out->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+    memset(probe_out, 0, sizeof(*probe_out)); memset(unnest_out, 0, sizeof(*unnest_out));
   }
   // not the fine-partition path (small shard): nested tuples into a ctx-owned buffer, then the unnest of the pairs
   auto& hj = c->hj;

@@ -56,6 +56,8 @@ struct hj3d_ctx {
   int64_t packed_min_probe = 1ll << 22;     // smaller probe inputs use the other paths
   int64_t packed_slice_bytes = 100 << 10;   // shared memory of one k_probe_packed block: two blocks (+ static + reserved) per SM's 228 KB
   int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
+  void*   fused_hot_list = nullptr;          // hot list of the last fused probe + unnest call (arena memory)
+  uint32_t fused_hot_cap = 0;
   int     smem_optin = 0;                   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   // per-phase events of the last call
   cudaEvent_t ev[PH_COUNT][2];

@@ -19,12 +19,19 @@
 
 namespace hj3d {
 
+// A probe record whose group is longer than kUnnestWarpMax rows (skewed keys: one Zipf key owns millions of build rows): its
+// output range is reserved with the tile's, the copy is left to k_unnest_hot_groups, which spreads one group over many blocks.
+struct __align__(8) HotGroup { uint32_t left, start, len, pad; unsigned long long pos; };
+constexpr uint32_t kHotChunk = 8192;       // rows one block copies at a time
+constexpr uint32_t kHotSplit = 64;         // blocks that share one hot group
+
 template <int HASH, bool CHECKSUM, bool WRITE>
 __device__ __forceinline__ void probe_unnest_items(const Slot<typename HashT<HASH>::key_t>* __restrict__ in, uint32_t n_rec, const Dir& d,
                                                    uint32_t bucket_base, uint32_t nbk, const uint32_t* offp, uint32_t row_base,
                                                    const Group<typename HashT<HASH>::key_t>* grp, const uint32_t* __restrict__ rows,
                                                    uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr,
-                                                   ProbeAcc& acc, unsigned long long* wsum64, unsigned long long* sm_base) {
+                                                   ProbeAcc& acc, unsigned long long* wsum64, unsigned long long* sm_base,
+                                                   HotGroup* __restrict__ hot_list, uint32_t hot_cap, unsigned long long* hot_count) {
   using KeyT = typename HashT<HASH>::key_t;
   using SlotT = Slot<KeyT>;
   using GroupT = Group<KeyT>;
@@ -104,18 +111,15 @@ __device__ __forceinline__ void probe_unnest_items(const Slot<typename HashT<HAS
         pos += T;
       }
 #pragma unroll
-      for (int j = 0; j < IT; ++j) {                      // hot groups: the warp copies them one after the other
+      for (int j = 0; j < IT; ++j) {                      // hot groups: listed with their reserved output position, copied later
         uint32_t hot = __ballot_sync(0xffffffffu, len[j] > kUnnestWarpMax);
         while (hot) {
           const uint32_t s = __ffs(hot) - 1;
           hot &= hot - 1;
           const uint32_t L = __shfl_sync(0xffffffffu, len[j], s);
-          const uint32_t b = __shfl_sync(0xffffffffu, st[j], s);
-          const uint32_t lf = __shfl_sync(0xffffffffu, id[j], s);
-          for (uint32_t r = lane; r < L; r += 32) {
-            const uint32_t row = __ldg(rows + b + r);
-            if (CHECKSUM) { const uint64_t mx = pair_mix(lf, row); acc.sum += mx; acc.x ^= mx; }
-            if (WRITE && pos + r < out_cap) out[pos + r] = make_uint2(lf, row);
+          if (lane == s) {
+            const unsigned long long h = atomicAdd(hot_count, 1ull);
+            if (h < hot_cap) { HotGroup g; g.left = id[j]; g.start = st[j]; g.len = L; g.pad = 0; g.pos = pos; hot_list[h] = g; }
           }
           pos += L;
         }
@@ -130,7 +134,8 @@ __global__ void __launch_bounds__(kFineThreads, 3)
 k_probe_nested_unnest(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs, Dir d, FineCfg fc, const uint2* __restrict__ work,
                       const uint32_t* __restrict__ work_part, const uint32_t* __restrict__ goff,
                       const Group<typename HashT<HASH>::key_t>* __restrict__ groups, const uint32_t* __restrict__ rows,
-                      uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
+                      uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr,
+                      HotGroup* __restrict__ hot_list, uint32_t hot_cap, unsigned long long* hot_count) {
   using KeyT = typename HashT<HASH>::key_t;
   using GroupT = Group<KeyT>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,9 +159,29 @@ k_probe_nested_unnest(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs
   __syncthreads();
   ProbeAcc acc;
   const Slot<KeyT>* in = recs + w.x;
-  if (fits) probe_unnest_items<HASH, CHECKSUM, WRITE>(in, w.y, d, d.lo + blo, nbk, sm_off, glo, sm_groups, rows, out, out_cap, ctr, acc, wsum64, &sm_base);
-  else      probe_unnest_items<HASH, CHECKSUM, WRITE>(in, w.y, d, d.lo + blo, nbk, goff + blo, 0u, groups, rows, out, out_cap, ctr, acc, wsum64, &sm_base);
+  if (fits) probe_unnest_items<HASH, CHECKSUM, WRITE>(in, w.y, d, d.lo + blo, nbk, sm_off, glo, sm_groups, rows, out, out_cap, ctr, acc, wsum64, &sm_base, hot_list, hot_cap, hot_count);
+  else      probe_unnest_items<HASH, CHECKSUM, WRITE>(in, w.y, d, d.lo + blo, nbk, goff + blo, 0u, groups, rows, out, out_cap, ctr, acc, wsum64, &sm_base, hot_list, hot_cap, hot_count);
   commit_acc(acc, ctr, CHECKSUM);
+}
+
+// the listed hot groups: group e is copied by the kHotSplit blocks (e, 0..kHotSplit), kHotChunk rows at a time
+template <bool CHECKSUM, bool WRITE>
+__global__ void __launch_bounds__(256)
+k_unnest_hot_groups(const HotGroup* __restrict__ hot_list, uint32_t n_hot, const uint32_t* __restrict__ rows,
+                    uint2* __restrict__ out, unsigned long long out_cap, DevCounters* ctr) {
+  ProbeAcc acc;
+  for (uint32_t e = blockIdx.x; e < n_hot; e += gridDim.x) {
+    const HotGroup g = hot_list[e];
+    for (uint32_t c0 = blockIdx.y * kHotChunk; c0 < g.len; c0 += kHotSplit * kHotChunk) {
+      const uint32_t c1 = c0 + kHotChunk < g.len ? c0 + kHotChunk : g.len;
+      for (uint32_t r = c0 + threadIdx.x; r < c1; r += 256) {
+        const uint32_t row = __ldg(rows + g.start + r);
+        if (CHECKSUM) { const uint64_t mx = pair_mix(g.left, row); acc.sum += mx; acc.x ^= mx; }
+        if (WRITE && g.pos + r < out_cap) out[g.pos + r] = make_uint2(g.left, row);
+      }
+    }
+  }
+  if (CHECKSUM) commit_acc(acc, ctr, true);
 }
 
 }  // namespace hj3d
