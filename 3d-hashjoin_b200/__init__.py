@@ -128,6 +128,11 @@ class Parts:
         return {"n_records": int(n.value), "n_sent_remote": int(sent.value), "bucket_lo": int(lo.value), "bucket_hi": int(hi.value),
                 "overflow": int(ov.value)}
 
+    def selected(self):
+        n = C.c_uint64()
+        capi.check(self.lib.hj3d_parts_selected(self.h, C.byref(n)))
+        return int(n.value)
+
     def destroy(self):
         if getattr(self, "h", None):
             self.lib.hj3d_parts_destroy(self.h)
@@ -179,8 +184,14 @@ class Comm:
         capi.check(self.lib.hj3d_comm_shard(self.h, int(num_buckets), C.byref(lo), C.byref(hi)))
         return int(lo.value), int(hi.value)
 
-    def begin(self, slot, tuples, n, ks, num_buckets, rowid_base, flags=0):
-        capi.check(self.lib.hj3d_exchange_begin(self.h, slot, _ptr(tuples), int(n), ks, int(num_buckets), int(rowid_base), flags))
+    def begin(self, slot, tuples, n, ks, num_buckets, rowid_base, flags=0, selection=None):
+        """selection: (attr_offset, op, constant) with op 1 <, 2 <=, 3 >, 4 >=, 5 ==, 6 != on an int32 attribute (fused AlgSelection)"""
+        if selection is None:
+            capi.check(self.lib.hj3d_exchange_begin(self.h, slot, _ptr(tuples), int(n), ks, int(num_buckets), int(rowid_base), flags))
+        else:
+            sel = capi.Selection(*selection)
+            capi.check(self.lib.hj3d_exchange_begin_select(self.h, slot, _ptr(tuples), int(n), ks, int(num_buckets), int(rowid_base), flags,
+                                                           C.byref(sel)))
 
     def end(self, slot, tuples, rowid_base, rowid_bound=0):
         """returns (rc, Parts); rc == OVERFLOW: a receive region overflowed somewhere (retry with XCHG_EXACT / more room)"""

@@ -36,7 +36,7 @@ SYMBOLS = [
     "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_probe2_unnest2", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
     "hj3d_comm_unique_id", "hj3d_comm_create", "hj3d_comm_create_local", "hj3d_comm_set_option", "hj3d_comm_destroy",
-    "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
+    "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_begin_select", "hj3d_parts_selected", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
     "hj3d_table_build_parts", "hj3d_probe_parts",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
     "hj3d_gen_column_u32",
@@ -54,6 +54,10 @@ class KeySpec(C.Structure):
 
     def __init__(self, tuple_bytes, key_offset, key_bytes=4, hash_id=HASH_MURMUR32, rowid_offset=NO_ROWID):
         super().__init__(tuple_bytes, key_offset, key_bytes, hash_id, rowid_offset)
+
+
+class Selection(C.Structure):
+    _fields_ = [("attr_offset", C.c_uint32), ("op", C.c_uint32), ("constant", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -133,6 +137,8 @@ def load():
     L.hj3d_comm_reserve.argtypes = [vp, i32, u64, u32]
     L.hj3d_comm_shard.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_exchange_begin.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32]
+    L.hj3d_exchange_begin_select.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32, C.POINTER(Selection)]
+    L.hj3d_parts_selected.argtypes = [vp, C.POINTER(u64)]
     L.hj3d_exchange_end.argtypes = [vp, i32, vp, u32, u64, C.POINTER(vp)]
     L.hj3d_parts_info.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
     L.hj3d_parts_destroy.argtypes = [vp]

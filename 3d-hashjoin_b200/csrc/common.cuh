@@ -32,6 +32,7 @@ __host__ __device__ __forceinline__ uint64_t pair_mix(uint32_t l, uint32_t r) {
 // 64-bit remainder for 64-bit hashes, a mask when numBuckets is a power of two.
 struct Dir {
   uint64_t magic;      // ceil(2^64 / D) (0 for D == 1)
+  uint64_t magic64;    // floor((2^64 - 1) / D): Barrett quotient estimate for 64-bit hashes
   uint32_t D;          // global number of buckets
   uint32_t pow2_mask;  // D - 1 if D is a power of two else 0xFFFFFFFF marker via is_pow2
   uint32_t is_pow2;
@@ -45,6 +46,7 @@ inline Dir make_dir(uint64_t D, uint64_t lo, uint64_t hi) {
   d.is_pow2 = (D & (D - 1)) == 0;
   d.pow2_mask = (uint32_t)(D - 1);
   d.magic = D == 1 ? 0 : (0xFFFFFFFFFFFFFFFFull / D + 1);
+  d.magic64 = 0xFFFFFFFFFFFFFFFFull / D;
   d.lo = (uint32_t)lo;
   d.n_local = (uint32_t)(hi - lo);
   return d;
@@ -57,7 +59,13 @@ __device__ __forceinline__ uint32_t mod_u32(uint32_t h, const Dir& d) {
 }
 __device__ __forceinline__ uint32_t mod_u64(uint64_t h, const Dir& d) {
   if (d.is_pow2) return (uint32_t)h & d.pow2_mask;
-  return (uint32_t)(h % (uint64_t)d.D);
+  // Barrett: q = floor(h * floor((2^64-1)/D) / 2^64) underestimates floor(h / D) by at most 2 (a hardware 64-bit `%` is a
+  // ~100 instruction subroutine and the nested build / probe evaluate the bucket several times per tuple)
+  const uint64_t q = __umul64hi(h, d.magic64);
+  uint64_t r = h - q * (uint64_t)d.D;
+  if (r >= d.D) r -= d.D;
+  if (r >= d.D) r -= d.D;
+  return (uint32_t)r;
 }
 
 // Key/hash traits per hash id.
@@ -92,7 +100,25 @@ struct Src {
   uint32_t        stride;
   uint32_t        key_off;
   uint32_t        rowid_off;  // HJ3D_NO_ROWID: row id = position
+  // optional selection fused into the load (AlgSelection, algebra.hh:279-315): tuples whose int32 attribute at sel_off does
+  // not satisfy `attr <op> sel_cst` are dropped by the partition / exchange pass (sel_op 0 = none)
+  uint32_t        sel_off = 0, sel_op = 0;
+  int32_t         sel_cst = 0;
 };
+
+__device__ __forceinline__ bool src_selected(const Src& s, uint64_t i) {
+  if (s.sel_op == 0) return true;
+  const uint64_t idx = s.gather ? (uint64_t)__ldg(s.gather + i) : i;
+  const int32_t v = __ldg(reinterpret_cast<const int32_t*>(s.base + idx * s.stride + s.sel_off));
+  switch (s.sel_op) {
+    case 1: return v < s.sel_cst;
+    case 2: return v <= s.sel_cst;
+    case 3: return v > s.sel_cst;
+    case 4: return v >= s.sel_cst;
+    case 5: return v == s.sel_cst;
+    default: return v != s.sel_cst;
+  }
+}
 
 // A block's work: records [t0, t0 + tn).  tilemap == nullptr: block b owns tile b of the whole input;
 // otherwise the input is bucket-range partitioned with gaps and tilemap[b] = (first record, count).

@@ -125,6 +125,7 @@ struct hj3d_parts {
   unsigned long long* d_count = nullptr; // device [n_ranges * n_src]
   uint64_t n_total = 0;                  // records received
   uint64_t n_sent_remote = 0;            // records this rank wrote into other GPUs' buffers
+  uint64_t n_local_selected = 0;         // tuples of this rank's slice that passed the fused selection (all of them without one)
   uint64_t rowid_bound = 0;              // global relation size (row ids are global positions)
   int      overflow = 0;                 // a segment exceeded its capacity
 };

@@ -94,6 +94,7 @@ struct hj3d_comm {
   uint64_t n_local[kSlots] = {0, 0};
   bool exact[kSlots] = {false, false};
   bool pending[kSlots] = {false, false};
+  hj3d_selection sel[kSlots] = {};
   void* h_pinned = nullptr;                      // world * kMaxRanges * 8 bytes
 };
 
@@ -349,8 +350,16 @@ int hj3d_comm_shard(hj3d_comm* cm, uint64_t D, uint64_t* lo, uint64_t* hi) {
   return HJ3D_OK;
 }
 
+int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
+                               uint32_t flags, const hj3d_selection* sel);
+
 int hj3d_exchange_begin(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
                         uint32_t flags) {
+  return hj3d_exchange_begin_select(cm, slot, d_tuples, n, ks, D, rowid_base, flags, nullptr);
+}
+
+int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
+                               uint32_t flags, const hj3d_selection* sel) {
   if (!cm || slot < 0 || slot >= kSlots) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
   if (!D || D > 0xFFFFFFFFull) return fail(HJ3D_ERR_INVALID, "bad num_buckets");
   if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
@@ -370,6 +379,12 @@ int hj3d_exchange_begin(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t 
   cm->cap_seg[slot] = (min_recv / ((uint64_t)pl.rpo * cm->world)) & ~1ull;
   if (!cm->exact[slot] && cm->cap_seg[slot] < 2) return fail(HJ3D_ERR_INVALID, "receive buffer too small for the range x source regions");
   Src src = make_src(d_tuples, n, ks, nullptr);
+  cm->sel[slot] = hj3d_selection{0, 0, 0};
+  if (sel && sel->op) {
+    if (sel->op > 6 || sel->attr_offset % 4 || sel->attr_offset + 4 > ks.tuple_bytes) return fail(HJ3D_ERR_INVALID, "bad selection");
+    cm->sel[slot] = *sel;
+    src.sel_off = sel->attr_offset; src.sel_op = sel->op; src.sel_cst = sel->constant;
+  }
   PhaseTimer pt(c, PH_PARTITION);
   CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
   int rc = HJ3D_OK;
@@ -421,6 +436,7 @@ static int exact_second_pass(hj3d_comm* cm, int slot, const void* d_tuples, uint
   CUDA_TRY(cudaMemcpyAsync(cm->d_pstart[slot], h_ps, ((size_t)pl.n_ranges + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
   Src src = make_src(d_tuples, cm->n_local[slot], cm->ks[slot], nullptr);
+  src.sel_off = cm->sel[slot].attr_offset; src.sel_op = cm->sel[slot].op; src.sel_cst = cm->sel[slot].constant;
   int rc;
   switch (cm->ks[slot].hash_id) {
     case HJ3D_HASH_MURMUR32: rc = launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, ~0ull); break;
@@ -463,7 +479,7 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaGetLastError());
   // host view: what I received, what I sent to others, overflow of any region anybody wrote (every rank sees all counts)
-  uint64_t recv = 0, sent = 0; int overflow = 0;
+  uint64_t recv = 0, sent = 0, mine = 0; int overflow = 0;
   for (int s = 0; s < cm->world; ++s)
     for (uint32_t q = 0; q < pl.n_ranges; ++q) {
       const uint64_t cnt = h_all[(size_t)s * kMaxRanges + q];
@@ -472,11 +488,18 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
       const uint64_t stored = (!cm->exact[slot] && cnt > cm->cap_seg[slot]) ? cm->cap_seg[slot] : cnt;
       if (owner == cm->rank) recv += stored;
       if (s == cm->rank && owner != cm->rank) sent += stored;
+      if (s == cm->rank) mine += cnt;
     }
-  parts->n_total = recv; parts->n_sent_remote = sent; parts->overflow = overflow;
+  parts->n_total = recv; parts->n_sent_remote = sent; parts->n_local_selected = mine; parts->overflow = overflow;
   cm->pending[slot] = false;
   *out = parts.release();
   return overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+int hj3d_parts_selected(hj3d_parts* p, uint64_t* n_local_selected) {
+  if (!p || !n_local_selected) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  *n_local_selected = p->n_local_selected;
+  return HJ3D_OK;
 }
 
 int hj3d_parts_info(hj3d_parts* p, uint64_t* n_records, uint64_t* n_sent_remote, uint64_t* bucket_lo, uint64_t* bucket_hi, int* overflow) {

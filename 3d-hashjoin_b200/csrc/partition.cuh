@@ -69,7 +69,7 @@ k_part_hist(Src s, Dir d, PartFn pf, uint32_t n_parts, unsigned long long* __res
   for (int j = 0; j < kPartItems; ++j) {
     const uint64_t i = base + (uint64_t)j * kPartThreads;
     uint32_t p = 0xFFFFFFFFu;
-    if (i < s.n) p = pf(HashT<HASH>::bucket(src_key<KeyT>(s, i), d));
+    if (i < s.n && src_selected(s, i)) p = pf(HashT<HASH>::bucket(src_key<KeyT>(s, i), d));
     const bool valid = p < n_parts;
     if (n_parts <= 8) {
       const uint32_t peers = peers_small(valid ? p : 0u, valid);
@@ -170,6 +170,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   // ---- load the tile's keys (and ids): all loads are issued before the first use
   KeyT     key[ITEMS];
   uint32_t id[ITEMS];
+  uint32_t dropmask = 0;
   // (ncu: the generic loads below -- 64-bit index arithmetic, gather / row-id checks and a bounds check per tuple -- were
   //  31 % of the level-1 kernel's instructions; full tiles of a plain row store take the short paths)
   if (RECS && tn == (uint32_t)TILE) {
@@ -184,7 +185,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
       key[j] = 0; id[j] = 0;
       if (li < tn) { const SlotT r = in[li]; key[j] = r.key; id[j] = r.rowid; }
     }
-  } else if (!s.gather && s.rowid_off == HJ3D_NO_ROWID && tn == (uint32_t)TILE) {
+  } else if (!s.gather && s.rowid_off == HJ3D_NO_ROWID && tn == (uint32_t)TILE && s.sel_op == 0) {
     const uint8_t* p0 = s.base + (t0 + threadIdx.x) * (uint64_t)s.stride + s.key_off;
     const uint32_t step = (uint32_t)THREADS * s.stride;
     const uint32_t id0 = (uint32_t)t0 + threadIdx.x + (LEFTID ? 0u : rowid_base);
@@ -201,6 +202,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
       if (li < tn) {
         key[j] = src_key<KeyT>(s, t0 + li);
         id[j] = LEFTID ? src_leftid(s, t0 + li) : src_rowid(s, t0 + li) + rowid_base;
+        if (!src_selected(s, t0 + li)) dropmask |= 1u << j;             // fused AlgSelection: the tuple joins no partition
       }
     }
   }
@@ -226,7 +228,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
     const uint32_t li = j * THREADS + threadIdx.x;
     pr[j] = 0xFFFFFFFFu;
     uint32_t lp = 0xFFFFFFFFu;
-    if (li < tn) {
+    if (li < tn && !((dropmask >> j) & 1u)) {
       const uint32_t q = part_of(key[j]);
       if (q < n_parts && q - q0 < fan) lp = q - q0;
     }

@@ -713,6 +713,164 @@ def run_config3(args):
                       "unit": "ms per step (build S + build T + probe strand)", "n_gpus": 1, "steps": 3, "warmup": 2, "points": rows}), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ config 5: main_algebra_example pipeline
+def run_config5(args):
+    """BASELINE config 5: the operator pipeline of main_algebra_example's algebra_test2 (main_algebra_example.cc:265-347) at scale
+    and across N GPUs:   scan L -> select (L.b < 40) -> nested probe (L.a = R.c) -> unnest -> count,   nested 3D table built on R.
+    int32 attributes hashed with murmur64 of the sign-extended key (main_algebra_example.cc:53-65), 8-byte tuples; R.c are
+    foreign keys into L.a (Zipf with --zipf, else uniform), L.a unique.  The selection is evaluated inside the exchange /
+    partition kernel's load (hj3d_exchange_begin_select); probe + unnest run as one fused kernel."""
+    import torch
+    import hj3d_loader
+    pkg = hj3d_loader.load()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = pkg.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    lib = pkg.capi.load()
+    nL, nR = 1 << args.log2_build, 1 << args.log2_probe
+    nLl, nRl = nL // world, nR // world
+    SEL_CONST = 40
+    L = torch.zeros((nLl, 2), dtype=torch.int32, device=dev)
+    R = torch.zeros((nRl, 2), dtype=torch.int32, device=dev)
+    ctx.gen_column(L, 8, 0, rank * nLl, nLl, pkg.capi.GEN_PERMUTATION, vmax=nL, seed=SEED_R)          # L.a: unique keys
+    ctx.gen_column(L, 8, 4, rank * nLl, nLl, pkg.capi.GEN_UNIFORM, vmax=100, seed=7)                    # L.b: selection attribute
+    ctx.gen_column(R, 8, 0, rank * nRl, nRl, pkg.capi.GEN_ZIPF if args.zipf > 0 else pkg.capi.GEN_UNIFORM, vmax=nL, zipf_q=args.zipf, seed=SEED_S)
+    ctx.gen_column(R, 8, 4, rank * nRl, nRl, pkg.capi.GEN_IOTA)
+    ks = pkg.KeySpec(8, 0, 4, pkg.HASH_MURMUR64_SEXT32)
+
+    def all_sum(vals):
+        if dist is None:
+            return [int(v) for v in vals]
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in vals], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        return [int(x) & M64 for x in t.tolist()]
+
+    def all_xor(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v], dtype=torch.int64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        x = 0
+        for o in out:
+            x ^= int(o.item()) & M64
+        return x
+    present = torch.zeros(nL, dtype=torch.uint8, device=dev)
+    present[R[:, 0].to(torch.int64)] = 1
+    if dist is not None:
+        dist.all_reduce(present, op=dist.ReduceOp.MAX)
+    D = max(int(present.sum(dtype=torch.int64).item()), 1)                    # #distinct R.c
+    del present
+    # expected result: every R row whose partner in L passes the selection gives one (L row, R row) pair
+    La = torch.zeros((nL, 1), dtype=torch.int32, device=dev); Lb = torch.zeros((nL, 1), dtype=torch.int32, device=dev)
+    ctx.gen_column(La, 4, 0, 0, nL, pkg.capi.GEN_PERMUTATION, vmax=nL, seed=SEED_R)
+    ctx.gen_column(Lb, 4, 0, 0, nL, pkg.capi.GEN_UNIFORM, vmax=100, seed=7)
+    inv = torch.empty(nL, dtype=torch.int64, device=dev)
+    inv[La[:, 0].to(torch.int64)] = torch.arange(nL, dtype=torch.int64, device=dev)
+    sel_total = int((Lb[:, 0] < SEL_CONST).sum().item())
+    e_sum, e_xor, e_cnt = 0, 0, 0
+    for lo in range(0, nRl, 1 << 26):
+        hi = min(nRl, lo + (1 << 26))
+        lrow = inv[R[lo:hi, 0].to(torch.int64)]
+        keep = Lb[lrow, 0] < SEL_CONST
+        rrow = torch.arange(rank * nRl + lo, rank * nRl + hi, dtype=torch.int64, device=dev)
+        s_, x_ = torch_pair_checksum(torch, lrow[keep], rrow[keep])
+        e_sum = (e_sum + s_) & M64; e_xor ^= x_; e_cnt += int(keep.sum().item())
+    del La, Lb, inv
+    torch.cuda.empty_cache()
+    e_sum, e_cnt = all_sum([e_sum, e_cnt]); e_xor = all_xor(e_xor)
+
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if world > 1:
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(pkg.Comm.unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        comm = pkg.Comm.create(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
+    else:
+        comm = pkg.Comm.create(ctx, 1, 0, None)
+    slack = 1.25 if args.zipf <= 0 else float(max(world, 1))
+    comm.reserve(0, int(nR / world * slack) + (1 << 20), 4)
+    comm.reserve(1, int(nL / world * 1.25) + (1 << 20), 4)
+    lo_, hi_ = comm.shard(D)
+    table = ctx.table(pkg.NESTED, D, shard=(lo_, hi_))
+    cap_out = e_cnt if (args.zipf > 0 or world == 1) else int(e_cnt / world * 1.3) + 4096
+    out = torch.empty((max(cap_out, 1), 2), dtype=torch.int32, device=dev)
+    xflags = pkg.capi.XCHG_EXACT if args.zipf > 0 else 0
+    state = {}
+
+    def step(fl=0):
+        table.clear()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        comm.begin(0, R, nRl, ks, D, rank * nRl, xflags)
+        comm.begin(1, L, nLl, ks, D, rank * nLl, xflags, selection=(4, 1, SEL_CONST))      # AlgSelection: L.b < 40, inside the load
+        rc0, pr = comm.end(0, R, rank * nRl, nR)
+        rc1, plp = comm.end(1, L, rank * nLl, nL)
+        ev[1].record()
+        assert rc0 == 0 and rc1 == 0, "exchange region overflow"
+        table.build_parts(pr)
+        tb = ctx.timings()
+        rc, c, u = table.probe_parts(plp, 3, flags=fl, out=out, out_cap=cap_out)
+        tp = ctx.timings()
+        ev[2].record()
+        assert rc == 0, "result buffer overflow"
+        state.update(tb=tb, tp=tp)
+        state.update(ev=ev, sel=plp.selected(), probe=c, unnest=u, sent=8 * (pr.info()["n_sent_remote"] + plp.info()["n_sent_remote"]))
+        pr.destroy(); plp.destroy()
+        return u
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    u0 = step(pkg.F_CHECKSUM)
+    g_sum, g_cnt, g_sel, g_probe = all_sum([u0["checksum_sum"], u0["out_tuples"], state["sel"], state["probe"]["matches"]])
+    g_xor = all_xor(u0["checksum_xor"])
+    verified = bool((g_sum, g_xor, g_cnt, g_sel) == (e_sum, e_xor, e_cnt, sel_total))
+    assert verified, f"pipeline result differs from the independent torch computation: {(g_sum, g_xor, g_cnt, g_sel)} vs {(e_sum, e_xor, e_cnt, sel_total)}"
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        x_ms = state["ev"][0].elapsed_time(state["ev"][1]); j_ms = state["ev"][1].elapsed_time(state["ev"][2])
+        print(json.dumps({"metric": "config 5: pipeline input tuples/sec (scan -> select -> nested 3D probe -> unnest -> count)",
+                          "value": (nL + nR) / (ms * 1e-3), "unit": "tuples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "dtype": "i32 keys, murmur64 of the sign-extended key",
+                          "data": "synthetic (device generated, identical at every N)",
+                          "config": {"workload": f"main_algebra_example algebra_test2 shape: |L| = 2^{args.log2_build} (unique a, selection b < 40 of uniform [0,100)), "
+                                                 f"|R| = 2^{args.log2_probe} ({'Zipf s=' + str(args.zipf) if args.zipf > 0 else 'uniform'} foreign keys c), "
+                                                 f"nested table on R with {D} buckets", "parallelism": f"bucket-range sharding over {world} GPU(s)"},
+                          "counters": {"c_scan_L": nL, "c_select": g_sel, "c_probe": g_probe, "c_unnest": g_cnt, "c_top": g_cnt, "c_build_R": nR},
+                          "result": {"verified_checksum_and_counts": verified},
+                          "phases_ms": {"exchange_both_relations": x_ms, "build_probe_unnest": j_ms,
+                                        "build": {k: state["tb"][k] for k in ("partition_ms", "group_ms", "total_ms")},
+                                        "probe": {k: state["tp"][k] for k in ("partition_ms", "probe_ms", "unnest_ms", "total_ms")}},
+                          "shuffle": {"bytes_sent_per_gpu": state["sent"], "bus_gbs_per_gpu": state["sent"] / (x_ms * 1e-3) / 1e9 if x_ms > 0 else None}}), flush=True)
+    sync_all()
+    comm.destroy()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -734,11 +892,13 @@ def main():
     ap.add_argument("--checksum", action="store_true",
                     help="also fold the result checksum inside the TIMED steps (it is always verified once, untimed)")
     ap.add_argument("--opt", action="append", default=[], help="engine option id=value (HJ3D_OPT_*), repeatable")
-    ap.add_argument("--config", type=int, default=2, help="2 = the headline KFK join (default); 3 = main_experiment4 duplicate sweep (N=1)")
+    ap.add_argument("--config", type=int, default=2, help="2 = the headline KFK join (default); 3 = main_experiment4 duplicate sweep (N=1); 5 = main_algebra_example pipeline (scan/select/3D join/unnest/count) on N GPUs")
     ap.add_argument("--c3-points", action="append", default=[], help="config 3 point log2R,alpha,beta,A,B (repeatable)")
     args = ap.parse_args()
     if args.config == 3:
         return run_config3(args)
+    if args.config == 5:
+        return run_config5(args)
     if args.impl == "reference":
         run_reference(args)
     else:

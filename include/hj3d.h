@@ -287,6 +287,13 @@ int hj3d_comm_destroy(hj3d_comm* comm);
 int hj3d_comm_reserve(hj3d_comm* comm, int slot, uint64_t records, uint32_t key_bytes);
 /* bucket range [lo, hi) this rank owns in a num_buckets wide directory: create its table with hj3d_table_create_shard */
 int hj3d_comm_shard(hj3d_comm* comm, uint64_t num_buckets, uint64_t* lo, uint64_t* hi);
+/* AlgSelection (algebra.hh:279-315) fused into the exchange's load: only tuples whose int32 attribute at attr_offset satisfies
+ * `attr <op> constant` take part (op: 1 <, 2 <=, 3 >, 4 >=, 5 ==, 6 !=; 0 = no selection).  hj3d_parts_selected reports how
+ * many tuples of this rank's slice passed (AlgSelection::count()). */
+typedef struct { uint32_t attr_offset; uint32_t op; int32_t constant; } hj3d_selection;
+int hj3d_exchange_begin_select(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
+                               uint32_t rowid_base, uint32_t flags, const hj3d_selection* selection);
+int hj3d_parts_selected(hj3d_parts* parts, uint64_t* n_local_selected);
 int hj3d_exchange_begin(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
                         uint32_t rowid_base, uint32_t flags);
 /* d_tuples / rowid_base: the same as in _begin (the exact mode reads the slice a second time); rowid_bound: global relation
