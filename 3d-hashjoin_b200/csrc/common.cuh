@@ -32,7 +32,6 @@ __host__ __device__ __forceinline__ uint64_t pair_mix(uint32_t l, uint32_t r) {
 // 64-bit remainder for 64-bit hashes, a mask when numBuckets is a power of two.
 struct Dir {
   uint64_t magic;      // ceil(2^64 / D) (0 for D == 1)
-  uint64_t magic64;    // floor((2^64 - 1) / D): Barrett quotient estimate for 64-bit hashes
   uint32_t D;          // global number of buckets
   uint32_t pow2_mask;  // D - 1 if D is a power of two else 0xFFFFFFFF marker via is_pow2
   uint32_t is_pow2;
@@ -46,7 +45,6 @@ inline Dir make_dir(uint64_t D, uint64_t lo, uint64_t hi) {
   d.is_pow2 = (D & (D - 1)) == 0;
   d.pow2_mask = (uint32_t)(D - 1);
   d.magic = D == 1 ? 0 : (0xFFFFFFFFFFFFFFFFull / D + 1);
-  d.magic64 = 0xFFFFFFFFFFFFFFFFull / D;
   d.lo = (uint32_t)lo;
   d.n_local = (uint32_t)(hi - lo);
   return d;
@@ -61,7 +59,7 @@ __device__ __forceinline__ uint32_t mod_u64(uint64_t h, const Dir& d) {
   if (d.is_pow2) return (uint32_t)h & d.pow2_mask;
   // Barrett: q = floor(h * floor((2^64-1)/D) / 2^64) underestimates floor(h / D) by at most 2 (a hardware 64-bit `%` is a
   // ~100 instruction subroutine and the nested build / probe evaluate the bucket several times per tuple)
-  const uint64_t q = __umul64hi(h, d.magic64);
+  const uint64_t q = __umul64hi(h, d.magic - 1ull);                     // magic = ceil(2^64 / D) = floor((2^64-1)/D) + 1 for D not a power of two
   uint64_t r = h - q * (uint64_t)d.D;
   if (r >= d.D) r -= d.D;
   if (r >= d.D) r -= d.D;

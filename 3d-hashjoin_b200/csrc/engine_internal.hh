@@ -186,7 +186,7 @@ static inline void dev_free(hj3d_ctx*, void*) {}   // arena memory is reclaimed 
 
 template <class T> int buf_ensure(hj3d_ctx* c, Buf& b, T** p, uint64_t count) {
   if (count == 0) count = 1;
-  const size_t bytes = count * sizeof(T);
+  const size_t bytes = count * sizeof(T) + 64;              // + padding: bulk copies round a slice's size up to 16 bytes
   if (b.cap < bytes) {
     if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     HJ_TRY(raw_alloc(&b.p, bytes));

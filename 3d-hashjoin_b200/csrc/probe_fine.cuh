@@ -190,14 +190,35 @@ k_probe_fine(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs, Dir d, 
   const uint32_t nrows = rhi - rlo;
   const uint32_t pre = sizeof(RowT) >= 16 ? 0u : (rlo & (uint32_t)(16 / sizeof(RowT) - 1));   // copy from the 16-byte aligned predecessor
   const uint32_t off_bytes = ((nbk + 1) * 4 + 15) & ~15u;
-  const bool fits = (uint64_t)off_bytes + (uint64_t)(nrows + pre) * sizeof(RowT) <= fc.smem_bytes;
+  // The slice arrives by two bulk asynchronous copies (TMA engine: cp.async.bulk, completion on an mbarrier) issued by ONE
+  // thread -- no LDG / STS pairs, no per-thread address arithmetic.  The engine needs 16-byte aligned addresses and sizes: the
+  // rows are copied from their 16-byte aligned predecessor on (`pre`), sizes are rounded up (the table's arrays are padded),
+  // and a slice whose directory words are not 16-byte aligned (fine partitions of fewer than 4 buckets: test configurations
+  // only) takes the global-memory path like a slice that does not fit.
+  constexpr bool kBulk = sizeof(RowT) == 8 || sizeof(RowT) == 16;      // 24-byte group records (64-bit keys) are not 16-byte aligned
+  const uint32_t row_bytes = ((nrows + pre) * (uint32_t)sizeof(RowT) + 15u) & ~15u;
+  const bool fits = (uint64_t)off_bytes + (uint64_t)row_bytes <= fc.smem_bytes && (!kBulk || (((uintptr_t)(off + blo)) & 15u) == 0);
   uint32_t* sm_off = reinterpret_cast<uint32_t*>(smem_raw);
   RowT*     sm_rows = reinterpret_cast<RowT*>(smem_raw + off_bytes);
-  if (fits) {
-    copy_to_smem(sm_off, off + blo, (nbk + 1) * 4);
-    copy_to_smem(sm_rows, rows + (rlo - pre), (nrows + pre) * (uint32_t)sizeof(RowT));
+  __shared__ unsigned long long sm_bar;
+  if (kBulk) {
+    if (fits && threadIdx.x == 0) mbar_init(&sm_bar, 1);
+    __syncthreads();
+    if (fits) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&sm_bar, off_bytes + row_bytes);
+        bulk_g2s(sm_off, off + blo, off_bytes, &sm_bar);
+        if (row_bytes) bulk_g2s(sm_rows, rows + (rlo - pre), row_bytes, &sm_bar);
+      }
+      mbar_wait(&sm_bar, 0);
+    }
+  } else {
+    if (fits) {
+      copy_to_smem(sm_off, off + blo, (nbk + 1) * 4);
+      copy_to_smem(sm_rows, rows + (rlo - pre), (nrows + pre) * (uint32_t)sizeof(RowT));
+    }
+    __syncthreads();
   }
-  __syncthreads();
   ProbeAcc acc;
   const Slot<KeyT>* in = recs + w.x;
   if (fits) probe_fine_items<HASH, KIND, CHECKSUM, WRITE, RowT>(in, w.y, d, d.lo + blo, nbk, sm_off, rlo - pre, sm_rows, out, out_cap, ctr, acc, wsum, &sm_base);

@@ -17,6 +17,7 @@
 // tile code against the global arrays.
 #pragma once
 
+#include "bulk_copy.cuh"
 #include "common.cuh"
 #include "probe.cuh"
 
@@ -49,6 +50,34 @@ __device__ __forceinline__ void copy_to_smem(void* dst, const void* src, uint32_
   } else {
     for (uint32_t i = threadIdx.x * 4; i < bytes; i += blockDim.x * 4)
       *reinterpret_cast<uint32_t*>(d + i) = __ldg(reinterpret_cast<const uint32_t*>(s + i));
+  }
+}
+
+// Stage a fine partition's slice -- its directory words and its rows -- in shared memory.  When the four addresses are
+// 16-byte aligned both ranges arrive by bulk asynchronous copies (TMA engine, mbarrier completion; sizes rounded up to 16:
+// the engine pads its arrays) issued by ONE thread; otherwise by the vector-load loop.  Called by all threads of the block;
+// returns with the data visible to all of them.
+__device__ __forceinline__ void stage_slice(void* dst_a, const void* src_a, uint32_t bytes_a, void* dst_b, const void* src_b,
+                                            uint32_t bytes_b, unsigned long long* bar) {
+  const uint32_t ra = (bytes_a + 15u) & ~15u, rb = (bytes_b + 15u) & ~15u;
+#ifdef HJ3D_NO_BULK
+  const bool bulk = false;
+#else
+  const bool bulk = ((((uintptr_t)src_a) | ((uintptr_t)src_b) | ((uintptr_t)dst_a) | ((uintptr_t)dst_b)) & 15u) == 0;   // block uniform
+#endif
+  if (bulk) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, ra + rb);
+      if (ra) bulk_g2s(dst_a, src_a, ra, bar);
+      if (rb) bulk_g2s(dst_b, src_b, rb, bar);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    copy_to_smem(dst_a, src_a, bytes_a);
+    copy_to_smem(dst_b, src_b, bytes_b);
+    __syncthreads();
   }
 }
 

@@ -152,11 +152,12 @@ k_probe_nested_unnest(const Slot<typename HashT<HASH>::key_t>* __restrict__ recs
   const bool fits = (uint64_t)off_bytes + (uint64_t)ngr * sizeof(GroupT) <= fc.smem_bytes;
   uint32_t* sm_off = reinterpret_cast<uint32_t*>(smem_raw);
   GroupT*   sm_groups = reinterpret_cast<GroupT*>(smem_raw + off_bytes);
+  __shared__ unsigned long long sm_bar;
   if (fits) {
-    copy_to_smem(sm_off, goff + blo, (nbk + 1) * 4);
-    copy_to_smem(sm_groups, groups + glo, ngr * (uint32_t)sizeof(GroupT));
+    stage_slice(sm_off, goff + blo, (nbk + 1) * 4, sm_groups, groups + glo, ngr * (uint32_t)sizeof(GroupT), &sm_bar);
+  } else {
+    __syncthreads();
   }
-  __syncthreads();
   ProbeAcc acc;
   const Slot<KeyT>* in = recs + w.x;
   if (fits) probe_unnest_items<HASH, CHECKSUM, WRITE>(in, w.y, d, d.lo + blo, nbk, sm_off, glo, sm_groups, rows, out, out_cap, ctr, acc, wsum64, &sm_base, hot_list, hot_cap, hot_count);
