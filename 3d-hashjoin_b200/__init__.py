@@ -193,6 +193,18 @@ class Comm:
             capi.check(self.lib.hj3d_exchange_begin_select(self.h, slot, _ptr(tuples), int(n), ks, int(num_buckets), int(rowid_base), flags,
                                                            C.byref(sel)))
 
+    def begin_host(self, slot, h_tuples, n, ks, num_buckets, rowid_base, flags=0, selection=None):
+        """the slice is a HOST buffer (numpy array / pinned torch CPU tensor / raw address): chunked upload, level 1 per chunk"""
+        a = h_tuples
+        hp = None if a is None else C.c_void_p(a) if isinstance(a, int) else C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") \
+            else a.ctypes.data_as(C.c_void_p)
+        sel = C.byref(capi.Selection(*selection)) if selection is not None else None
+        capi.check(self.lib.hj3d_exchange_begin_host(self.h, slot, hp, int(n), ks, int(num_buckets), int(rowid_base), flags, sel))
+
+    def append(self, slot, tuples, n, rowid_base, flags=0):
+        """next chunk of a slice begun with XCHG_MORE; the last chunk comes without the flag"""
+        capi.check(self.lib.hj3d_exchange_append(self.h, slot, _ptr(tuples), int(n), int(rowid_base), flags))
+
     def end(self, slot, tuples, rowid_base, rowid_bound=0):
         """returns (rc, Parts); rc == OVERFLOW: a receive region overflowed somewhere (retry with XCHG_EXACT / more room)"""
         h = C.c_void_p()

@@ -11,6 +11,8 @@
 
 #include "build.cuh"
 #include "build_nested_fine.cuh"
+#include <chrono>
+
 #include "engine_internal.hh"
 #include "partition.cuh"
 #include "probe.cuh"
@@ -1061,6 +1063,9 @@ int hj3d_ctx_destroy(hj3d_ctx* c) {
   if (!c) return HJ3D_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->host_comm) hj3d_comm_destroy(c->host_comm);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (cudaEvent_t e : c->chunk_ev) cudaEventDestroy(e);
   for (int i = 0; i < PH_COUNT; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
   cudaEventDestroy(c->ev_total[0]); cudaEventDestroy(c->ev_total[1]);
   cudaFree(c->d_ctr); cudaFree(c->d_stats); cudaFree(c->d_scalar); cudaFreeHost(c->h_pinned);
@@ -1097,6 +1102,7 @@ int hj3d_ctx_set_option(hj3d_ctx* c, int opt, int64_t v) {
     case HJ3D_OPT_PART_RANK_MATCH: c->part_rank_match = v != 0; break;
     case HJ3D_OPT_PROBE_THREADS: if (v == 256 || v == 512) c->probe_threads = v; break;
     case HJ3D_OPT_LEAN_PROBE: c->lean_probe = v != 0; break;
+    case HJ3D_OPT_HOST_CHUNK_BYTES: if (v >= 0) c->host_chunk_bytes = v; break;
     case HJ3D_OPT_PACKED_PROBE: c->packed_probe = v != 0; break;
     case HJ3D_OPT_PACKED_MIN_PROBE: c->packed_min_probe = v; break;
     case HJ3D_OPT_PACKED_SLICE_BYTES: if (v >= 1024 && v <= (110 << 10)) c->packed_slice_bytes = v & ~15ll; break;
@@ -1604,20 +1610,72 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
     return HJ3D_OK;
   };
   auto& hj = c->hj;
+  const bool trace = getenv("HJ3D_TRACE_HOST") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (trace) fprintf(stderr, "[join_host] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
+  // Streamed upload: the build relation goes up first on the copy stream, the probe relation follows in chunks; every probe
+  // chunk goes through partition level 1 (a one-rank exchange, hj3d_exchange_begin_host) as soon as it has landed, under the
+  // upload of the chunks behind it, and the table is built meanwhile on the caller's stream.  What is left after the last
+  // byte is partition level 2 and the probe kernel.
+  const uint64_t chunk_rows = c->host_chunk_bytes > 0 ? std::max<uint64_t>(1, (uint64_t)c->host_chunk_bytes / ksP.tuple_bytes) : 0;
+  bool streamed = chunk_rows && nP >= 2 * chunk_rows && nP <= 0xFFFFFFF0ull && D <= 0xFFFFFFFFull;
   HJ_TRY(ensure(&hj.b, &hj.cb, nB * ksB.tuple_bytes));
-  HJ_TRY(ensure(&hj.p, &hj.cp, nP * ksP.tuple_bytes));
-  if (nB) CUDA_TRY(cudaMemcpyAsync(hj.b, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
-  if (nP) CUDA_TRY(cudaMemcpyAsync(hj.p, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (streamed) {
+    if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    if (!c->host_comm) HJ_TRY(hj3d_comm_create(c, 1, 0, nullptr, &c->host_comm));
+    if (c->chunk_ev.empty()) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); c->chunk_ev.push_back(e); }
+    const uint64_t want = nP + nP / 24 + (4ull << 20);          // 256 regions of n/256 + 4 % + 16 K records
+    if (c->host_comm_records < want || c->host_comm_key_bytes != ksP.key_bytes) {
+      HJ_TRY(hj3d_comm_reserve(c->host_comm, 1, want, ksP.key_bytes));
+      c->host_comm_records = want; c->host_comm_key_bytes = ksP.key_bytes;
+    }
+    // the copy stream starts where the caller's stream is now (hj.b may still be read by an earlier call's kernels)
+    CUDA_TRY(cudaEventRecord(c->chunk_ev[0], c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->chunk_ev[0], 0));
+    if (nB) CUDA_TRY(cudaMemcpyAsync(hj.b, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->chunk_ev[0], c->copy_stream));
+    HJ_TRY(hj3d_exchange_begin_host(c->host_comm, 1, h_probe, nP, ksP, D, 0, 0, nullptr));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->chunk_ev[0], 0));
+    stamp("copies enqueued");
+  } else {
+    HJ_TRY(ensure(&hj.p, &hj.cp, nP * ksP.tuple_bytes));
+    if (nB) CUDA_TRY(cudaMemcpyAsync(hj.b, h_build, nB * ksB.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (nP) CUDA_TRY(cudaMemcpyAsync(hj.p, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream));
+  }
   hj3d_table* t = nullptr;
   HJ_TRY(hj3d_table_create(c, mode <= 1 ? HJ3D_CHAINING : HJ3D_NESTED, D, &t));
+  auto bail = [&](int code) {
+    if (streamed) cudaDeviceSynchronize();                    // nothing of this call may still be in flight on the side streams
+    hj3d_table_destroy(c, t);
+    return code;
+  };
   int rc = hj3d_table_build(c, t, hj.b, nB, ksB);
-  if (rc < 0) { hj3d_table_destroy(c, t); return rc; }
+  if (rc < 0) return bail(rc);
+  stamp("table built");
   const bool want_pairs = h_out != nullptr || (flags & HJ3D_F_DEVICE_RESULT);
   uint64_t n_out = 0;
   uint32_t* dOut = nullptr;
-  auto bail = [&](int code) { hj3d_table_destroy(c, t); return code; };
   if (want_pairs) { rc = ensure(&hj.out, &hj.cout, cap * 8); if (rc < 0) return bail(rc); dOut = (uint32_t*)hj.out; }
-  if (mode <= 1) {
+  hj3d_parts* parts = nullptr;
+  if (streamed) {
+    rc = hj3d_exchange_end(c->host_comm, 1, nullptr, 0, nP, &parts);
+    stamp("exchange_end");
+    if (rc < 0) { hj3d_parts_destroy(parts); return bail(rc); }
+    if (rc == HJ3D_OVERFLOW) {     // skewed keys overflowed a fixed region: upload again in one piece and take the general path
+      hj3d_parts_destroy(parts); parts = nullptr; streamed = false;
+      rc = ensure(&hj.p, &hj.cp, nP * ksP.tuple_bytes); if (rc < 0) return bail(rc);
+      cudaError_t e = cudaMemcpyAsync(hj.p, h_probe, nP * ksP.tuple_bytes, cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) return bail(fail(HJ3D_ERR_CUDA, cudaGetErrorString(e)));
+    }
+  }
+  if (parts) {
+    rc = hj3d_probe_parts(c, t, parts, mode, flags, dOut, cap, pc, uc);
+    hj3d_parts_destroy(parts);
+    if (rc < 0) return bail(rc);
+    n_out = mode == 3 ? uc->out_written : pc->out_written;
+  } else if (mode <= 1) {
     rc = hj3d_probe_chaining(c, t, hj.p, nP, ksP, nullptr, mode == 1, flags, dOut, cap, pc);
     if (rc < 0) return bail(rc);
     n_out = pc->out_written;
@@ -1630,6 +1688,7 @@ int hj3d_join_host(hj3d_ctx* c, int mode,
     if (rc < 0) return bail(rc);
     n_out = uc->out_written;
   }
+  stamp("probe done");
   const int final_rc = rc;
   if (h_out && n_out) {
     cudaError_t e = cudaMemcpyAsync(h_out, dOut, n_out * 8, cudaMemcpyDeviceToHost, c->stream);

@@ -55,6 +55,7 @@ struct hj3d_ctx {
                                             // kernel is issue bound at 7.0 ms against 5.4 ms for k_probe_fine
   int64_t packed_min_probe = 1ll << 22;     // smaller probe inputs use the other paths
   int64_t packed_slice_bytes = 100 << 10;   // shared memory of one k_probe_packed block: two blocks (+ static + reserved) per SM's 228 KB
+  int64_t host_chunk_bytes = 256ll << 20;   // hj3d_join_host: probe-side upload chunk (0 = one copy)
   int64_t lean_probe = 1;                   // at-most-one-result probes of fine partitions use k_probe_fine (probe_fine.cuh)
   void*   fused_hot_list = nullptr;          // hot list of the last fused probe + unnest call (arena memory)
   uint32_t fused_hot_cap = 0;
@@ -76,6 +77,12 @@ struct hj3d_ctx {
   std::vector<Chunk> arena;
   struct HostJoinBufs { void *b = nullptr, *p = nullptr, *out = nullptr, *nest = nullptr, *l = nullptr, *g = nullptr;
                         size_t cb = 0, cp = 0, cout = 0, cnest = 0, cl = 0, cg = 0; } hj;
+  // streamed upload of hj3d_join_host: copy stream, one event per chunk, a one-rank exchange (partition level 1 per chunk)
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> chunk_ev;
+  struct hj3d_comm* host_comm = nullptr;
+  uint64_t host_comm_records = 0;
+  uint32_t host_comm_key_bytes = 0;
 };
 
 struct Buf {  // persistent, grow-only device buffer owned by a table

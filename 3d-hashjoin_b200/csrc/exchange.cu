@@ -94,6 +94,17 @@ struct hj3d_comm {
   uint64_t n_local[kSlots] = {0, 0};
   bool exact[kSlots] = {false, false};
   bool pending[kSlots] = {false, false};
+  bool streaming[kSlots] = {false, false};       // HJ3D_XCHG_MORE: further chunks of the local slice follow (hj3d_exchange_append)
+  // host-resident slices (hj3d_exchange_begin_host): chunked upload on the ctx's copy stream into a comm-owned staging buffer,
+  // one event per chunk, level 1 per chunk on the comm's own exchange stream (the caller's stream stays free until _end)
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t ev_fence = nullptr;
+  cudaEvent_t ev_ready[kSlots] = {nullptr, nullptr};             // counts gathered (NCCL) / scatter finished, on xstream
+  std::vector<cudaEvent_t> chunk_ev[kSlots];
+  size_t n_chunks[kSlots] = {0, 0};
+  void*  stage[kSlots] = {nullptr, nullptr};
+  size_t stage_bytes[kSlots] = {0, 0};
+  bool   host_streamed[kSlots] = {false, false};
   hj3d_selection sel[kSlots] = {};
   void* h_pinned = nullptr;                      // world * kMaxRanges * 8 bytes
 };
@@ -144,9 +155,10 @@ __global__ void k_xchg_segments(const unsigned long long* __restrict__ all, uint
 }
 
 template <int HASH>
-int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap) {
+int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap, cudaStream_t st = nullptr) {
   using KeyT = typename HashT<HASH>::key_t;
   hj3d_ctx* c = cm->ctx;
+  if (!st) st = c->stream;
   const ExchangePlan& pl = cm->plan[slot];
   constexpr int TH = 512;
   const int kTile = TH * PartCfg<KeyT>::kItems;
@@ -160,7 +172,7 @@ int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsign
   const size_t sm = part_smem_bytes<KeyT>(pl.n_ranges, TH, false);
   auto kfn = k_part_scatter<HASH, false, false, TH, false, true>;
   CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  kfn<<<nb, TH, sm, c->stream>>>(src, nullptr, d, pf, pl.n_ranges, pl.n_ranges, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot],
+  kfn<<<nb, TH, sm, st>>>(src, nullptr, d, pf, pl.n_ranges, pl.n_ranges, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot],
                                  (Slot<KeyT>*)nullptr, peer);
   ++c->launches;
   CUDA_TRY(cudaGetLastError());
@@ -180,14 +192,15 @@ int launch_hist(hj3d_comm* cm, int slot, Src src) {
 }
 
 // everybody's counts of this slot -> d_all (also the barrier: a rank's contribution leaves after its scatter kernel)
-int gather_counts(hj3d_comm* cm, int slot) {
+int gather_counts(hj3d_comm* cm, int slot, cudaStream_t st = nullptr) {
   hj3d_ctx* c = cm->ctx;
   if (cm->nc) {
-    NCCL_TRY(nccl().AllGather(cm->d_cursor[slot], cm->d_all[slot], kMaxRanges, ncclUint64, cm->nc, c->stream));
+    NCCL_TRY(nccl().AllGather(cm->d_cursor[slot], cm->d_all[slot], kMaxRanges, ncclUint64, cm->nc, st ? st : c->stream));
     return HJ3D_OK;
   }
   for (hj3d_comm* o : cm->group->ranks) {       // single process: wait for every rank's kernel, then copy its counts over
-    if (o != cm) CUDA_TRY(cudaStreamWaitEvent(c->stream, o->ev_scatter[slot], 0));
+    if (!o) continue;
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, o->ev_scatter[slot], 0));       // (a rank's own scatter may have run on its exchange stream)
     CUDA_TRY(cudaMemcpyAsync(cm->d_all[slot] + (size_t)o->rank * kMaxRanges, o->d_cursor[slot], kMaxRanges * 8, cudaMemcpyDefault, c->stream));
   }
   return HJ3D_OK;
@@ -210,7 +223,9 @@ int comm_alloc_state(hj3d_comm* cm) {
     CUDA_TRY(cudaMalloc((void**)&cm->d_all[s], (size_t)cm->world * kMaxRanges * 8));
     CUDA_TRY(cudaMalloc((void**)&cm->d_pstart[s], (kMaxRanges + 1) * 8));
     CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_scatter[s], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_ready[s], cudaEventDisableTiming));
   }
+  CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_fence, cudaEventDisableTiming));
   CUDA_TRY(cudaMalloc((void**)&cm->d_bar, (1 + kMaxPeers) * 8));
   CUDA_TRY(cudaMemset(cm->d_bar, 0, (1 + kMaxPeers) * 8));
   CUDA_TRY(cudaMallocHost(&cm->h_pinned, (size_t)(cm->world + 1) * kMaxRanges * 8));
@@ -291,11 +306,18 @@ int hj3d_comm_destroy(hj3d_comm* cm) {
   if (!cm) return HJ3D_OK;
   cudaSetDevice(cm->ctx->device);
   cudaStreamSynchronize(cm->ctx->stream);
+  if (cm->ctx->copy_stream) cudaStreamSynchronize(cm->ctx->copy_stream);
+  if (cm->xstream) cudaStreamSynchronize(cm->xstream);
   for (int s = 0; s < kSlots; ++s) {
     free_slot(cm, s);
     cudaFree(cm->d_cursor[s]); cudaFree(cm->d_all[s]); cudaFree(cm->d_pstart[s]);
     if (cm->ev_scatter[s]) cudaEventDestroy(cm->ev_scatter[s]);
+    if (cm->ev_ready[s]) cudaEventDestroy(cm->ev_ready[s]);
+    for (cudaEvent_t e : cm->chunk_ev[s]) cudaEventDestroy(e);
+    cudaFree(cm->stage[s]);
   }
+  if (cm->ev_fence) cudaEventDestroy(cm->ev_fence);
+  if (cm->xstream) { cudaStreamSynchronize(cm->xstream); cudaStreamDestroy(cm->xstream); }
   cudaFree(cm->d_bar);
   if (cm->h_pinned) cudaFreeHost(cm->h_pinned);
   if (cm->nc) nccl().CommDestroy(cm->nc);
@@ -358,18 +380,17 @@ int hj3d_exchange_begin(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t 
   return hj3d_exchange_begin_select(cm, slot, d_tuples, n, ks, D, rowid_base, flags, nullptr);
 }
 
-int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
-                               uint32_t flags, const hj3d_selection* sel) {
+// what _begin, _begin_select and _begin_host share: argument checks, the plan and the uniform regions of this slot
+static int prepare_slot(hj3d_comm* cm, int slot, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t flags, const hj3d_selection* sel) {
   if (!cm || slot < 0 || slot >= kSlots) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
   if (!D || D > 0xFFFFFFFFull) return fail(HJ3D_ERR_INVALID, "bad num_buckets");
-  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
   if (n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 tuples per rank");
   HJ_TRY(check_keyspec(ks));
-  hj3d_ctx* c = cm->ctx;
   const uint32_t rb = ks.key_bytes == 8 ? 16 : 8;
   if (!cm->recv[slot] || cm->rec_bytes[slot] != rb) return fail(HJ3D_ERR_INVALID, "hj3d_comm_reserve has not been called for this slot / key width");
   for (int r = 0; r < cm->world; ++r) if (!cm->peer_recv[slot][r]) return fail(HJ3D_ERR_INVALID, "a peer has not reserved its receive buffer yet");
-  CUDA_TRY(cudaSetDevice(c->device));
+  if ((flags & HJ3D_XCHG_EXACT) && (flags & HJ3D_XCHG_MORE)) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_EXACT reads the slice twice: it cannot be streamed");
+  if (sel && sel->op && (sel->op > 6 || sel->attr_offset % 4 || sel->attr_offset + 4 > ks.tuple_bytes)) return fail(HJ3D_ERR_INVALID, "bad selection");
   ExchangePlan& pl = cm->plan[slot];
   pl = make_plan(cm, D);
   cm->ks[slot] = ks; cm->n_local[slot] = n; cm->exact[slot] = (flags & HJ3D_XCHG_EXACT) != 0;
@@ -378,24 +399,40 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
   if (cm->group) for (hj3d_comm* o : cm->group->ranks) if (o && o->recv_records[slot] < min_recv) min_recv = o->recv_records[slot];
   cm->cap_seg[slot] = (min_recv / ((uint64_t)pl.rpo * cm->world)) & ~1ull;
   if (!cm->exact[slot] && cm->cap_seg[slot] < 2) return fail(HJ3D_ERR_INVALID, "receive buffer too small for the range x source regions");
-  Src src = make_src(d_tuples, n, ks, nullptr);
-  cm->sel[slot] = hj3d_selection{0, 0, 0};
-  if (sel && sel->op) {
-    if (sel->op > 6 || sel->attr_offset % 4 || sel->attr_offset + 4 > ks.tuple_bytes) return fail(HJ3D_ERR_INVALID, "bad selection");
-    cm->sel[slot] = *sel;
-    src.sel_off = sel->attr_offset; src.sel_op = sel->op; src.sel_cst = sel->constant;
+  cm->sel[slot] = (sel && sel->op) ? *sel : hj3d_selection{0, 0, 0};
+  return HJ3D_OK;
+}
+
+static Src slot_src(const hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n) {
+  Src src = make_src(d_tuples, n, cm->ks[slot], nullptr);
+  src.sel_off = cm->sel[slot].attr_offset; src.sel_op = cm->sel[slot].op; src.sel_cst = cm->sel[slot].constant;
+  return src;
+}
+
+static int scatter_by_hash(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap, cudaStream_t st = nullptr) {
+  switch (cm->ks[slot].hash_id) {
+    case HJ3D_HASH_MURMUR32: return launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, cap, st);
+    case HJ3D_HASH_MURMUR64: return launch_scatter<HJ3D_HASH_MURMUR64>(cm, slot, src, rowid_base, cap, st);
+    default:                 return launch_scatter<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src, rowid_base, cap, st);
   }
+}
+
+int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
+                               uint32_t flags, const hj3d_selection* sel) {
+  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
+  HJ_TRY(prepare_slot(cm, slot, n, ks, D, flags, sel));
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const ExchangePlan& pl = cm->plan[slot];
+  const Src src = slot_src(cm, slot, d_tuples, n);
+  cm->host_streamed[slot] = false;
   PhaseTimer pt(c, PH_PARTITION);
   CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
   int rc = HJ3D_OK;
   if (!cm->exact[slot]) {
     k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, c->stream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
     ++c->launches;
-    switch (ks.hash_id) {
-      case HJ3D_HASH_MURMUR32: rc = launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
-      case HJ3D_HASH_MURMUR64: rc = launch_scatter<HJ3D_HASH_MURMUR64>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
-      default:                 rc = launch_scatter<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src, rowid_base, cm->cap_seg[slot]); break;
-    }
+    rc = scatter_by_hash(cm, slot, src, rowid_base, cm->cap_seg[slot]);
   } else {
     switch (ks.hash_id) {
       case HJ3D_HASH_MURMUR32: rc = launch_hist<HJ3D_HASH_MURMUR32>(cm, slot, src); break;
@@ -404,12 +441,80 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
     }
   }
   if (rc < 0) return rc;
+  cm->pending[slot] = true;
+  cm->streaming[slot] = (flags & HJ3D_XCHG_MORE) != 0;
+  if (cm->streaming[slot]) return HJ3D_OK;           // the counts leave with the last chunk
   CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
   if (cm->nc) HJ_TRY(gather_counts(cm, slot));       // multi-process: enqueue the all-gather right behind the kernel
-  cm->pending[slot] = true;
-  // exact mode keeps what it needs for the second pass
-  if (cm->exact[slot]) { cm->ks[slot] = ks; }
-  (void)rowid_base;
+  return HJ3D_OK;
+}
+
+// The local slice lives in HOST memory.  It is uploaded in chunks on the ctx's copy stream and every chunk goes through
+// level 1 on the comm's exchange stream as soon as it has landed, under the upload of the chunks behind it.  The caller's
+// stream is not touched before hj3d_exchange_end, so what it queues meanwhile (the build of the other relation) overlaps.
+int hj3d_exchange_begin_host(hj3d_comm* cm, int slot, const void* h_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
+                             uint32_t flags, const hj3d_selection* sel) {
+  if (n && !h_tuples) return fail(HJ3D_ERR_INVALID, "h_tuples == NULL");
+  if (flags & (HJ3D_XCHG_EXACT | HJ3D_XCHG_MORE)) return fail(HJ3D_ERR_UNSUPPORTED, "hj3d_exchange_begin_host streams the slice once: no HJ3D_XCHG_EXACT / _MORE");
+  HJ_TRY(prepare_slot(cm, slot, n, ks, D, flags, sel));
+  if ((uint64_t)rowid_base + n > 0xFFFFFFFFull) return fail(HJ3D_ERR_UNSUPPORTED, "row ids past 2^32");
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  if (!cm->xstream) CUDA_TRY(cudaStreamCreateWithFlags(&cm->xstream, cudaStreamNonBlocking));
+  const ExchangePlan& pl = cm->plan[slot];
+  const size_t bytes = (size_t)n * ks.tuple_bytes;
+  if (cm->stage_bytes[slot] < bytes) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); CUDA_TRY(cudaStreamSynchronize(cm->xstream)); CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    cudaFree(cm->stage[slot]); cm->stage[slot] = nullptr; cm->stage_bytes[slot] = 0;
+    HJ_TRY(raw_alloc(&cm->stage[slot], bytes));
+    cm->stage_bytes[slot] = bytes;
+  }
+  uint64_t chunk_rows = c->host_chunk_bytes > 0 ? std::max<uint64_t>(1, (uint64_t)c->host_chunk_bytes / ks.tuple_bytes) : n;
+  chunk_rows = std::max<uint64_t>(chunk_rows, (n + 4095) / 4096);                       // at most 4096 chunks
+  const size_t n_chunks = n ? (size_t)((n + chunk_rows - 1) / chunk_rows) : 0;
+  while (cm->chunk_ev[slot].size() < n_chunks) {
+    cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); cm->chunk_ev[slot].push_back(e);
+  }
+  // both side streams start where the caller's stream is now (the buffers of an earlier exchange may still be read there)
+  CUDA_TRY(cudaEventRecord(cm->ev_fence, c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, cm->ev_fence, 0));
+  CUDA_TRY(cudaStreamWaitEvent(cm->xstream, cm->ev_fence, 0));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, cm->xstream));
+  k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, cm->xstream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
+  ++c->launches;
+  for (size_t i = 0; i < n_chunks; ++i) {
+    const uint64_t r0 = i * chunk_rows, rn = std::min<uint64_t>(chunk_rows, n - r0);
+    uint8_t* d_chunk = (uint8_t*)cm->stage[slot] + r0 * ks.tuple_bytes;
+    CUDA_TRY(cudaMemcpyAsync(d_chunk, (const uint8_t*)h_tuples + r0 * ks.tuple_bytes, rn * ks.tuple_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(cm->chunk_ev[slot][i], c->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(cm->xstream, cm->chunk_ev[slot][i], 0));
+    HJ_TRY(scatter_by_hash(cm, slot, slot_src(cm, slot, d_chunk, rn), (uint32_t)(rowid_base + r0), cm->cap_seg[slot], cm->xstream));
+  }
+  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], cm->xstream));
+  if (cm->nc) HJ_TRY(gather_counts(cm, slot, cm->xstream));
+  CUDA_TRY(cudaEventRecord(cm->ev_ready[slot], cm->xstream));
+  cm->n_chunks[slot] = n_chunks;
+  cm->pending[slot] = true; cm->streaming[slot] = false; cm->host_streamed[slot] = true;
+  return HJ3D_OK;
+}
+
+// A further chunk of the local slice (streamed upload: a chunk is partitioned while the next one is still on its way
+// from the host).  The per-range cursors simply keep counting, so the chunks of one source share its regions.
+int hj3d_exchange_append(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, uint32_t rowid_base, uint32_t flags) {
+  if (!cm || slot < 0 || slot >= kSlots) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
+  if (!cm->pending[slot] || !cm->streaming[slot]) return fail(HJ3D_ERR_INVALID, "hj3d_exchange_append needs a hj3d_exchange_begin with HJ3D_XCHG_MORE");
+  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
+  if (cm->n_local[slot] + n > 0xFFFFFFF0ull) return fail(HJ3D_ERR_UNSUPPORTED, "more than 2^32-16 tuples per rank");
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int rc = scatter_by_hash(cm, slot, slot_src(cm, slot, d_tuples, n), rowid_base, cm->cap_seg[slot]);
+  if (rc < 0) return rc;
+  cm->n_local[slot] += n;
+  if (flags & HJ3D_XCHG_MORE) return HJ3D_OK;
+  cm->streaming[slot] = false;
+  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
+  if (cm->nc) HJ_TRY(gather_counts(cm, slot));
   return HJ3D_OK;
 }
 
@@ -435,14 +540,7 @@ static int exact_second_pass(hj3d_comm* cm, int slot, const void* d_tuples, uint
   h_ps[pl.n_ranges] = 0;
   CUDA_TRY(cudaMemcpyAsync(cm->d_pstart[slot], h_ps, ((size_t)pl.n_ranges + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
-  Src src = make_src(d_tuples, cm->n_local[slot], cm->ks[slot], nullptr);
-  src.sel_off = cm->sel[slot].attr_offset; src.sel_op = cm->sel[slot].op; src.sel_cst = cm->sel[slot].constant;
-  int rc;
-  switch (cm->ks[slot].hash_id) {
-    case HJ3D_HASH_MURMUR32: rc = launch_scatter<HJ3D_HASH_MURMUR32>(cm, slot, src, rowid_base, ~0ull); break;
-    case HJ3D_HASH_MURMUR64: rc = launch_scatter<HJ3D_HASH_MURMUR64>(cm, slot, src, rowid_base, ~0ull); break;
-    default:                 rc = launch_scatter<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, src, rowid_base, ~0ull); break;
-  }
+  const int rc = scatter_by_hash(cm, slot, slot_src(cm, slot, d_tuples, cm->n_local[slot]), rowid_base, ~0ull);
   if (rc < 0) return rc;
   CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
   return HJ3D_OK;
@@ -456,6 +554,19 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
   CUDA_TRY(cudaSetDevice(c->device));
   const ExchangePlan& pl = cm->plan[slot];
   unsigned long long* h_all = (unsigned long long*)cm->h_pinned;
+  if (cm->host_streamed[slot]) {
+    // Wait for the upload on the HOST before anything is queued on the caller's stream: the small copies below would sit
+    // behind the chunk events and share the copy engine's queue with the chunks in flight -- measured, that time-slices
+    // the upload down to 17..47 GB/s instead of 55.  Nothing is lost: this call synchronises anyway.
+    if (cm->n_chunks[slot]) CUDA_TRY(cudaEventSynchronize(cm->chunk_ev[slot][cm->n_chunks[slot] - 1]));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, cm->ev_ready[slot], 0));
+    cm->host_streamed[slot] = false;
+  }
+  if (cm->streaming[slot]) {                         // ended without a final append: the chunks so far are the slice
+    cm->streaming[slot] = false;
+    CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
+    if (cm->nc) HJ_TRY(gather_counts(cm, slot));
+  }
   if (!cm->nc) HJ_TRY(gather_counts(cm, slot));
   if (cm->exact[slot]) {
     if (cm->group && cm->group->ranks.size() > 1)

@@ -69,6 +69,8 @@ extern "C" {
 #define HJ3D_OPT_PACKED_PROBE    21 /* 0/1: unique chaining probes of large inputs run over compressed table slices (default 0) */
 #define HJ3D_OPT_PACKED_MIN_PROBE 22 /* probe inputs smaller than this use the other paths (default 2^22)                     */
 #define HJ3D_OPT_PACKED_SLICE_BYTES 23 /* shared memory of one compressed-slice probe block (default 100 KiB; tests shrink it) */
+#define HJ3D_OPT_HOST_CHUNK_BYTES 24 /* hj3d_join_host uploads the probe relation in pieces of this size and partitions each piece
+                                      * while the next one is in flight (default 256 MiB; 0 = one copy, then the join)        */
 #define HJ3D_OPT_UNNEST_HOT_CAP  19 /* entries of the unnest's hot-tuple list (default 2^20; tests shrink it)           */
 #define HJ3D_OPT_PART_SAMPLE     20 /* partition regions sized from a sampled histogram: 0 never, 1 after this ctx has seen
                                        an overflow (default), 2 always                                                */
@@ -245,7 +247,11 @@ int hj3d_split_pairs(hj3d_ctx* ctx, const uint32_t* d_pairs, uint64_t n, uint32_
  * One call = build strand + probe strand (+ unnest) of one plan, host->device copies of both
  * relations and the device->host copy of the result inside.  mode: 0 chaining, 1 chaining with
  * IsBuildKeyUnique, 2 nested (no unnest), 3 nested + unnest  (plans Crs/CsrUU, Csr, NrsNU, Nrs/Nsr
- * of main_experiment1.cc:624-1285).  h_out_pairs nullable.  stats nullable. */
+ * of main_experiment1.cc:624-1285).  h_out_pairs nullable.  stats nullable.
+ * The probe relation is uploaded in chunks (HJ3D_OPT_HOST_CHUNK_BYTES) on a second stream (hj3d_exchange_begin_host on a
+ * one-rank communicator); the build and the first partition pass of every chunk run under the upload of the following
+ * chunks, so the call costs the host-to-device transfer plus the second partition pass and the probe kernel.  Pinned host
+ * memory is needed for the overlap.  HJ3D_TRACE_HOST=1 in the environment prints host-side time stamps of the phases. */
 int hj3d_join_host(hj3d_ctx* ctx, int mode,
                    const void* h_build, uint64_t n_build, hj3d_keyspec ks_build, uint64_t num_buckets,
                    const void* h_probe, uint64_t n_probe, hj3d_keyspec ks_probe, uint32_t flags,
@@ -274,6 +280,8 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
  * flags: HJ3D_XCHG_EXACT = two passes (histogram first, regions packed at exact offsets): for skewed keys whose ranges
  *        overflow the uniform regions (hj3d_exchange_end returns HJ3D_OVERFLOW then; nothing is lost by retrying). */
 #define HJ3D_XCHG_EXACT 1u
+#define HJ3D_XCHG_MORE  2u /* streamed slice: further chunks follow through hj3d_exchange_append (the last one without this flag).
+                            * A chunk is partitioned while the next one is still being uploaded; not with HJ3D_XCHG_EXACT. */
 #define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256; 128 with more than one rank) */
 #define HJ3D_XOPT_MIN_RANGE_WIDTH 2 /* smallest range width in buckets (default 16384: a multiple of every fine-partition width) */
 typedef struct hj3d_comm  hj3d_comm;
@@ -296,6 +304,15 @@ int hj3d_exchange_begin_select(hj3d_comm* comm, int slot, const void* d_tuples, 
 int hj3d_parts_selected(hj3d_parts* parts, uint64_t* n_local_selected);
 int hj3d_exchange_begin(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
                         uint32_t rowid_base, uint32_t flags);
+/* next chunk of the local slice after a hj3d_exchange_begin(.., HJ3D_XCHG_MORE); rowid_base = global row id of its first tuple */
+int hj3d_exchange_append(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, uint32_t rowid_base, uint32_t flags);
+/* The local slice is in HOST memory (pinned, for the overlap): it is uploaded in chunks of HJ3D_OPT_HOST_CHUNK_BYTES on a copy
+ * stream and every chunk goes through the exchange (partition level 1, peer stores) as soon as it has landed, on a stream
+ * of the communicator -- the ctx's stream is not used before hj3d_exchange_end, so work queued on it meanwhile (building the
+ * table from the other relation) runs under the upload.  selection nullable.  No HJ3D_XCHG_EXACT / _MORE.  Pass
+ * d_tuples = NULL to hj3d_exchange_end. */
+int hj3d_exchange_begin_host(hj3d_comm* comm, int slot, const void* h_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
+                             uint32_t rowid_base, uint32_t flags, const hj3d_selection* selection);
 /* d_tuples / rowid_base: the same as in _begin (the exact mode reads the slice a second time); rowid_bound: global relation
  * size (0 = unknown).  Returns HJ3D_OVERFLOW if a region overflowed anywhere (every rank returns it). */
 int hj3d_exchange_end(hj3d_comm* comm, int slot, const void* d_tuples, uint32_t rowid_base, uint64_t rowid_bound, hj3d_parts** out);

@@ -300,6 +300,57 @@ def test_join_host_entry_point(pkg, ctx, oracle):
             assert np.array_equal(sorted_pairs(out[:pc["out_written"]]), sorted_pairs(o["pairs"]))
 
 
+def test_join_host_streamed_upload(pkg, ctx, oracle):
+    """hj3d_join_host with the probe relation uploaded in chunks (HJ3D_OPT_HOST_CHUNK_BYTES): every chunk goes through
+    partition level 1 (hj3d_exchange_begin / _append with HJ3D_XCHG_MORE on a one-rank communicator) as it lands, the
+    join continues from the coarse ranges.  Same results as the one-copy path and the reference, in every mode, for
+    32- and 64-bit keys, with a ragged last chunk; a hot key that overflows its range takes the general path."""
+    import torch
+    rng = np.random.default_rng(77)
+    nR, nS = 6000, 50011
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR, nS)
+    R8 = np.zeros((nR, 2), np.uint64); R8[:, 0] = rng.permutation(nR).astype(np.uint64) << np.uint64(20)
+    S8 = np.zeros((nS, 2), np.uint64); S8[:, 0] = np.arange(nS); S8[:, 1] = R8[rng.integers(0, nR, nS), 0]
+    try:
+        for chunk_rows in (1000, 7777):
+            for mode, (B, kb, P, kp, D) in {1: (R, 0, S, 4, nR), 0: (R, 0, S, 4, 3001), 3: (R, 0, S, 4, 3001), 2: (R, 0, S, 4, 3001)}.items():
+                ctx.set_option(pkg.capi.OPT_HOST_CHUNK_BYTES, 12 * chunk_rows)
+                o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(12, kb), D, P, pyo.KeySpec(12, kp))
+                out = np.zeros((nS, 2), np.uint32)
+                Pp = torch.from_numpy(P).pin_memory()
+                rc, pc, uc, st = ctx.join_host(mode, B, len(B), KSg(pkg, 12, kb), D, Pp.numpy(), len(P), KSg(pkg, 12, kp),
+                                               flags=pkg.F_CHECKSUM, h_out=out, out_cap=nS, want_stats=True)
+                assert rc == 0 and st == o["stats"]
+                assert pc["matches"] == o["probe"]["matches"] and pc["num_cmps"] == o["probe"]["num_cmps"]
+                if mode == 3:
+                    assert sub(uc) == sub(o["unnest"])
+                    assert np.array_equal(sorted_pairs(out[:uc["out_written"]]), sorted_pairs(o["pairs"]))
+                elif mode <= 1:
+                    assert sub(pc) == sub(o["probe"])
+                    assert np.array_equal(sorted_pairs(out[:pc["out_written"]]), sorted_pairs(o["pairs"]))
+        # 64-bit keys (16-byte tuples and records)
+        ctx.set_option(pkg.capi.OPT_HOST_CHUNK_BYTES, 16 * 3000)
+        ks8b, ks8p = (16, 0, 8, 1), (16, 8, 8, 1)
+        o = oracle_plan(oracle, pyo, 1, R8, pyo.KeySpec(*ks8b), nR, S8, pyo.KeySpec(*ks8p))
+        out = np.zeros((nS, 2), np.uint32)
+        rc, pc, uc, st = ctx.join_host(1, R8, nR, KSg(pkg, *ks8b), nR, S8, nS, KSg(pkg, *ks8p), flags=pkg.F_CHECKSUM, h_out=out, out_cap=nS,
+                                       want_stats=True)
+        assert rc == 0 and st == o["stats"] and sub(pc) == sub(o["probe"])
+        assert np.array_equal(sorted_pairs(out[:pc["out_written"]]), sorted_pairs(o["pairs"]))
+        # one hot key: its coarse range overflows the fixed region of the streamed exchange -> general path, same answer
+        nH, D = 620000, 1 << 18
+        H = np.zeros((nH, 3), np.uint32); H[:, 0] = np.arange(nH); H[:, 1] = 7
+        H[::1000, 1] = rng.integers(0, nR, len(H[::1000]))
+        ctx.set_option(pkg.capi.OPT_HOST_CHUNK_BYTES, 12 * 50000)
+        o = oracle_plan(oracle, pyo, 1, R, pyo.KeySpec(12, 0), D, H, pyo.KeySpec(12, 4))
+        rc, pc, uc, st = ctx.join_host(1, R, nR, KSg(pkg, 12, 0), D, H, nH, KSg(pkg, 12, 4), flags=pkg.F_CHECKSUM, h_out=None, out_cap=nH,
+                                       want_stats=True)
+        assert rc == 0 and st == o["stats"] and sub(pc) == sub(o["probe"])
+    finally:
+        ctx.set_option(pkg.capi.OPT_HOST_CHUNK_BYTES, 256 << 20)
+
+
 def test_partition_by_owner_and_sharded_join(pkg, ctx, oracle):
     """Multi-GPU sharding emulated on one device: partition both relations by bucket-range owner, build one
     shard table per owner from (key, global row id) records, probe each shard with its own partition,
@@ -406,13 +457,15 @@ def test_shard_table_built_from_an_unpartitioned_relation(pkg, ctx, oracle):
             assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"])), what
 
 
+@pytest.mark.parametrize("host", [False, True], ids=["device", "host"])
 @pytest.mark.parametrize("world", [1, 3, 4])
-def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world):
+def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world, host):
     """The multi-GPU data plane (csrc/exchange.cu) with all ranks in ONE process on one device (hj3d_comm_create_local):
     every rank partitions its slice of both relations by bucket range straight into the owners' receive buffers, builds
     its shard from what it received (hj3d_table_build_parts: the local join continues at partition level 2) and probes
     it; merged counters, statistics and the result multiset equal the unsharded reference result.  Small range widths
-    and engine thresholds force the fine-partition path, the compaction fallback and ranks that own nothing."""
+    and engine thresholds force the fine-partition path, the compaction fallback and ranks that own nothing.
+    host: the slices are host arrays streamed through hj3d_exchange_begin_host (chunked upload, level 1 per chunk)."""
     import torch
     import ctypes as C
     lib = pkg.capi.load()
@@ -423,6 +476,7 @@ def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world):
         S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR, nS)
         ctxs = [pkg.Context(0, stream=stream) for _ in range(world)]
         for c in ctxs:
+            c.set_option(pkg.capi.OPT_HOST_CHUNK_BYTES, 12 * 3333)
             if fine:   # force the shared-memory fine-partition paths at test sizes
                 c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0); c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
                 c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096); c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
@@ -445,15 +499,21 @@ def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world):
                 b0, b1 = sl(nB, r); p0, p1 = sl(nP, r)
                 tb, tp = vB[b0:b1].contiguous(), vP[p0:p1].contiguous()
                 slices.append((tb, b0, b1, tp, p0, p1))
-                cm.begin(0, tb, b1 - b0, KSg(pkg, 12, kb), D, b0)
-                cm.begin(1, tp, p1 - p0, KSg(pkg, 12, kp), D, p0)
+                if host:
+                    hb, hp_ = np.ascontiguousarray(B[b0:b1]), np.ascontiguousarray(P[p0:p1])
+                    slices[-1] += (hb, hp_)                  # keep the host slices alive until _end
+                    cm.begin_host(0, hb, b1 - b0, KSg(pkg, 12, kb), D, b0)
+                    cm.begin_host(1, hp_, p1 - p0, KSg(pkg, 12, kp), D, p0)
+                else:
+                    cm.begin(0, tb, b1 - b0, KSg(pkg, 12, kb), D, b0)
+                    cm.begin(1, tp, p1 - p0, KSg(pkg, 12, kp), D, p0)
             parts = (pkg.Stats * world)()
             tot = {"matches": 0, "num_cmps": 0}
             pairs, n_recv = [], 0
             for r, cm in enumerate(comms):
-                tb, b0, b1, tp, p0, p1 = slices[r]
-                rc, pb = cm.end(0, tb, b0, nB); assert rc == 0
-                rc, pp = cm.end(1, tp, p0, nP); assert rc == 0
+                tb, b0, b1, tp, p0, p1 = slices[r][:6]
+                rc, pb = cm.end(0, None if host else tb, b0, nB); assert rc == 0
+                rc, pp = cm.end(1, None if host else tp, p0, nP); assert rc == 0
                 n_recv += pb.info()["n_records"]
                 lo, hi = cm.shard(D)
                 assert (lo, hi) == (pb.info()["bucket_lo"], pb.info()["bucket_hi"])
