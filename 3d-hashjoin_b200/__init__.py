@@ -133,6 +133,12 @@ class Parts:
         capi.check(self.lib.hj3d_parts_selected(self.h, C.byref(n)))
         return int(n.value)
 
+    def hot(self):
+        """tuples of this rank's slice that stayed local as hot-key tuples (XCHG_HOT)"""
+        n = C.c_uint64()
+        capi.check(self.lib.hj3d_parts_hot(self.h, C.byref(n)))
+        return int(n.value)
+
     def destroy(self):
         if getattr(self, "h", None):
             self.lib.hj3d_parts_destroy(self.h)
@@ -200,6 +206,10 @@ class Comm:
             else a.ctypes.data_as(C.c_void_p)
         sel = C.byref(capi.Selection(*selection)) if selection is not None else None
         capi.check(self.lib.hj3d_exchange_begin_host(self.h, slot, hp, int(n), ks, int(num_buckets), int(rowid_base), flags, sel))
+
+    def hot_sample(self, slot, tuples, n, ks):
+        """hot-key replication, step 1 (every rank, before begin(.., flags=XCHG_HOT)): sample the relation for hot keys"""
+        capi.check(self.lib.hj3d_exchange_hot_sample(self.h, slot, _ptr(tuples), int(n), ks))
 
     def append(self, slot, tuples, n, rowid_base, flags=0):
         """next chunk of a slice begun with XCHG_MORE; the last chunk comes without the flag"""
@@ -269,6 +279,10 @@ class Table:
     def build_parts(self, parts):
         capi.check(self.lib.hj3d_table_build_parts(self.ctx.h, self.h, parts.h))
         return self
+
+    def hot_answers(self, parts, mode):
+        """hot-key replication, step 3 (every rank, once this table is built): the owners' answers for the hot keys"""
+        capi.check(self.lib.hj3d_parts_hot_answers(self.ctx.h, self.h, parts.h, mode))
 
     def probe_parts(self, parts, mode, flags=F_CHECKSUM, out=None, out_cap=0):
         """probe with an exchanged relation: mode 0 / 1 chaining (1 = IsBuildKeyUnique), 2 nested, 3 nested + unnest"""

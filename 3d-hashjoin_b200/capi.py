@@ -23,7 +23,7 @@ OPT_LEAN_PROBE = 18
 OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
 OPT_PACKED_PROBE, OPT_PACKED_MIN_PROBE, OPT_PACKED_SLICE_BYTES = 21, 22, 23
 GEN_IOTA, GEN_PERMUTATION, GEN_UNIFORM, GEN_ZIPF, GEN_CONST = 0, 1, 2, 3, 4
-XCHG_EXACT, XCHG_MORE = 1, 2
+XCHG_EXACT, XCHG_MORE, XCHG_HOT = 1, 2, 4
 OPT_HOST_CHUNK_BYTES = 24
 XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH = 1, 2
 
@@ -37,7 +37,7 @@ SYMBOLS = [
     "hj3d_probe_chaining", "hj3d_probe_nested", "hj3d_unnest", "hj3d_unnest_pairs", "hj3d_probe_nested_unnest", "hj3d_probe2_unnest2", "hj3d_group_first_row", "hj3d_gather_u32",
     "hj3d_split_pairs", "hj3d_join_host",
     "hj3d_comm_unique_id", "hj3d_comm_create", "hj3d_comm_create_local", "hj3d_comm_set_option", "hj3d_comm_destroy",
-    "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_append", "hj3d_exchange_begin_host", "hj3d_exchange_begin_select", "hj3d_parts_selected", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
+    "hj3d_comm_reserve", "hj3d_comm_shard", "hj3d_exchange_begin", "hj3d_exchange_append", "hj3d_exchange_begin_host", "hj3d_exchange_hot_sample", "hj3d_parts_hot_answers", "hj3d_parts_hot", "hj3d_exchange_begin_select", "hj3d_parts_selected", "hj3d_exchange_end", "hj3d_parts_info", "hj3d_parts_destroy",
     "hj3d_table_build_parts", "hj3d_probe_parts",
     "hj3d_partition_by_owner", "hj3d_owner_range", "hj3d_table_create_shard", "hj3d_stats_merge",
     "hj3d_gen_column_u32",
@@ -139,6 +139,9 @@ def load():
     L.hj3d_comm_shard.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.hj3d_exchange_begin.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32]
     L.hj3d_exchange_begin_host.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32, C.POINTER(Selection)]
+    L.hj3d_exchange_hot_sample.argtypes = [vp, i32, vp, u64, KeySpec]
+    L.hj3d_parts_hot_answers.argtypes = [vp, vp, vp, i32]
+    L.hj3d_parts_hot.argtypes = [vp, C.POINTER(u64)]
     L.hj3d_exchange_append.argtypes = [vp, i32, vp, u64, u32, u32]
     L.hj3d_exchange_begin_select.argtypes = [vp, i32, vp, u64, KeySpec, u64, u32, u32, C.POINTER(Selection)]
     L.hj3d_parts_selected.argtypes = [vp, C.POINTER(u64)]

@@ -14,6 +14,7 @@
 #include <chrono>
 
 #include "engine_internal.hh"
+#include "hot.cuh"
 #include "partition.cuh"
 #include "probe.cuh"
 #include "probe_smem.cuh"
@@ -1507,8 +1508,101 @@ int hj3d_table_build_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p) {
   return HJ3D_OK;
 }
 
+// hot-key replication, step 3: every rank looks the hot keys up in its shard; one all-reduce hands everybody the owners' answers
+int hj3d_parts_hot_answers(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode) {
+  if (!c || !t || !p) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  if (!p->comm) return fail(HJ3D_ERR_INVALID, "the relation was not exchanged with HJ3D_XCHG_HOT");
+  if (mode != 0 && mode != 1 && mode != 3) return fail(HJ3D_ERR_UNSUPPORTED, "hot-key replication serves probe modes 0, 1 and 3 (a nested tuple's group reference is local to its shard)");
+  if ((mode <= 1) != (t->kind == HJ3D_CHAINING)) return fail(HJ3D_ERR_INVALID, "probe mode does not match the table kind");
+  HJ_TRY(parts_fit_table(p, t));
+  HJ_TRY(table_matches(t, parts_ks(p)));
+  CUDA_TRY(cudaSetDevice(c->device));
+  HotAnswers* ans = (HotAnswers*)hj3d_comm_hot_ans_buffer(p->comm, p->slot);
+  CUDA_TRY(cudaMemsetAsync(ans, 0, sizeof(HotAnswers), c->stream));
+#define HJ_ANS(H) do { using KeyT = typename HashT<H>::key_t; const HotTable<KeyT>* ht = (const HotTable<KeyT>*)p->hot_table; \
+    if (mode == 0)      k_hot_answers_chaining<H, false><<<1, kHotMax, 0, c->stream>>>(ht, t->dir, t->off, (const Slot<KeyT>*)t->slots, ans); \
+    else if (mode == 1) k_hot_answers_chaining<H, true><<<1, kHotMax, 0, c->stream>>>(ht, t->dir, t->off, (const Slot<KeyT>*)t->slots, ans); \
+    else                k_hot_answers_nested<H><<<1, kHotMax, 0, c->stream>>>(ht, t->dir, t->goff, (const Group<KeyT>*)t->groups, t->rows, ans); } while (0)
+  if (t->n) {
+    switch (p->hash_id) {
+      case HJ3D_HASH_MURMUR32: HJ_ANS(HJ3D_HASH_MURMUR32); break;
+      case HJ3D_HASH_MURMUR64: HJ_ANS(HJ3D_HASH_MURMUR64); break;
+      default:                 HJ_ANS(HJ3D_HASH_MURMUR64_SEXT32); break;
+    }
+    ++c->launches;
+  }
+#undef HJ_ANS
+  CUDA_TRY(cudaGetLastError());
+  HJ_TRY(hj3d_comm_hot_reduce_begin(p->comm, p->slot));
+  p->hot_mode = mode;
+  return HJ3D_OK;
+}
+
+int hj3d_parts_hot(hj3d_parts* p, uint64_t* n_hot) {
+  if (!p || !n_hot) return fail(HJ3D_ERR_INVALID, "NULL argument");
+  *n_hot = p->hot_count;
+  return HJ3D_OK;
+}
+
+// step 4: the local hot segment against the all-reduced answers; its counters are added to what the regular probe reported
+static int hot_join(hj3d_ctx* c, hj3d_parts* p, int mode, uint32_t flags, uint2* out, uint64_t cap, hj3d_counters* probe_out, hj3d_counters* unnest_out) {
+  if (p->hot_mode != mode) return fail(HJ3D_ERR_INVALID, "hj3d_parts_hot_answers has not been called for this probe mode");
+  const void* d_sum = nullptr;
+  HJ_TRY(hj3d_comm_hot_reduce_end(p->comm, p->slot, &d_sum));
+  const HotAnswers* ans = (const HotAnswers*)d_sum;
+  hj3d_counters* res = mode == 3 ? unnest_out : probe_out;
+  const bool cs = flags & HJ3D_F_CHECKSUM, wr = out != nullptr;
+  const uint64_t base = wr ? res->out_written : 0;
+  DevCounters* h = (DevCounters*)c->h_pinned;
+  memset(h, 0, sizeof(DevCounters)); h->out_cursor = base;
+  CUDA_TRY(cudaMemcpyAsync(c->d_ctr, h, sizeof(DevCounters), cudaMemcpyHostToDevice, c->stream));
+  const uint32_t nb = (uint32_t)std::min<uint64_t>(blocks_for(p->hot_count, 256), (uint64_t)c->sm_count * 8);
+#define HJ_HJ(H, N, C, W) k_hot_join<H, N, C, W><<<nb, 256, 0, c->stream>>>((const Slot<typename HashT<H>::key_t>*)p->hot_recs, p->hot_count, \
+    (const HotTable<typename HashT<H>::key_t>*)p->hot_table, ans, out, cap, c->d_ctr)
+#define HJ_HJ2(H, N) do { if (cs) { if (wr) HJ_HJ(H, N, true, true); else HJ_HJ(H, N, true, false); } \
+                          else    { if (wr) HJ_HJ(H, N, false, true); else HJ_HJ(H, N, false, false); } } while (0)
+#define HJ_HJ3(H) do { if (mode == 3) HJ_HJ2(H, true); else HJ_HJ2(H, false); } while (0)
+  switch (p->hash_id) {
+    case HJ3D_HASH_MURMUR32: HJ_HJ3(HJ3D_HASH_MURMUR32); break;
+    case HJ3D_HASH_MURMUR64: HJ_HJ3(HJ3D_HASH_MURMUR64); break;
+    default:                 HJ_HJ3(HJ3D_HASH_MURMUR64_SEXT32); break;
+  }
+#undef HJ_HJ3
+#undef HJ_HJ2
+#undef HJ_HJ
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  uint32_t* h_many = (uint32_t*)((char*)c->h_pinned + 512);
+  CUDA_TRY(cudaMemcpyAsync(h, c->d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(h_many, &ans->too_many, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (*h_many) return fail(HJ3D_ERR_UNSUPPORTED, "a hot key has more than 8 build partners: exchange the probe side without HJ3D_XCHG_HOT");
+  probe_out->matches += h->matches; probe_out->out_tuples += h->matches; probe_out->num_cmps += h->num_cmps;
+  const uint64_t flat = h->out_cursor - base;
+  if (mode == 3) { unnest_out->matches += flat; unnest_out->out_tuples += flat; }
+  res->checksum_sum += h->checksum_sum; res->checksum_xor ^= h->checksum_xor;
+  if (wr) {
+    if (h->out_cursor > cap) res->overflow = 1;
+    res->out_written = h->out_cursor > cap ? cap : h->out_cursor;
+  }
+  return HJ3D_OK;
+}
+
+static int probe_parts_regular(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32_t flags, uint32_t* d_out, uint64_t cap,
+                               hj3d_counters* probe_out, hj3d_counters* unnest_out);
+
 int hj3d_probe_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32_t flags, uint32_t* d_out, uint64_t cap,
                      hj3d_counters* probe_out, hj3d_counters* unnest_out) {
+  if (p && p->comm && mode == 2) return fail(HJ3D_ERR_UNSUPPORTED, "hot-key replication serves probe modes 0, 1 and 3");
+  if (p && p->comm && p->hot_mode != mode) return fail(HJ3D_ERR_INVALID, "hj3d_parts_hot_answers has not been called for this probe mode");
+  int rc = probe_parts_regular(c, t, p, mode, flags, d_out, cap, probe_out, unnest_out);
+  if (rc < 0 || !p->comm) return rc;
+  if (p->hot_count) HJ_TRY(hot_join(c, p, mode, flags, (uint2*)d_out, cap, probe_out, unnest_out));
+  return (mode == 3 ? unnest_out : probe_out)->overflow ? HJ3D_OVERFLOW : HJ3D_OK;
+}
+
+static int probe_parts_regular(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32_t flags, uint32_t* d_out, uint64_t cap,
+                               hj3d_counters* probe_out, hj3d_counters* unnest_out) {
   if (!c || !t || !p || !probe_out) return fail(HJ3D_ERR_INVALID, "NULL argument");
   if (mode < 0 || mode > 3) return fail(HJ3D_ERR_INVALID, "mode must be 0..3");
   if (mode == 3 && !unnest_out) return fail(HJ3D_ERR_INVALID, "unnest_out == NULL");
@@ -1554,7 +1648,7 @@ int hj3d_probe_parts(hj3d_ctx* c, hj3d_table* t, hj3d_parts* p, int mode, uint32
     HJ_TRY(raw_alloc(&hj.nest, need));
     hj.cnest = need;
   }
-  rc = hj3d_probe_parts(c, t, p, 2, flags & ~HJ3D_F_CHECKSUM, (uint32_t*)hj.nest, p->n_total, probe_out, nullptr);
+  rc = probe_parts_regular(c, t, p, 2, flags & ~HJ3D_F_CHECKSUM, (uint32_t*)hj.nest, p->n_total, probe_out, nullptr);
   if (rc < 0) return rc;
   return hj3d_unnest_pairs(c, t, (const uint32_t*)hj.nest, probe_out->out_written, flags, d_out, cap, unnest_out);
 }

@@ -135,6 +135,13 @@ struct hj3d_parts {
   uint64_t n_local_selected = 0;         // tuples of this rank's slice that passed the fused selection (all of them without one)
   uint64_t rowid_bound = 0;              // global relation size (row ids are global positions)
   int      overflow = 0;                 // a segment exceeded its capacity
+  // hot-key probe replication (hot.cuh): tuples of hot keys never left this GPU
+  void*    hot_recs = nullptr;           // Slot<KeyT>[hot_count] (owned by the comm)
+  uint64_t hot_count = 0;
+  const void* hot_table = nullptr;       // device HotTable<KeyT>
+  struct hj3d_comm* comm = nullptr;
+  int      slot = 0;
+  int      hot_mode = -1;                // probe mode the answers were computed for (hj3d_parts_hot_answers)
 };
 
 struct PhaseTimer {
@@ -227,3 +234,9 @@ static inline Src make_src(const void* d_tuples, uint64_t n, const hj3d_keyspec&
   return s;
 }
 
+// exchange.cu, used by engine.cu for the hot-key answers (hot.cuh)
+extern "C" {
+void* hj3d_comm_hot_ans_buffer(hj3d_comm* comm, int slot);
+int   hj3d_comm_hot_reduce_begin(hj3d_comm* comm, int slot);
+int   hj3d_comm_hot_reduce_end(hj3d_comm* comm, int slot, const void** d_sum);
+}

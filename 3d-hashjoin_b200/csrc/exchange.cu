@@ -21,6 +21,7 @@
 #include <memory>
 
 #include "engine_internal.hh"
+#include "hot.cuh"
 #include "partition.cuh"
 
 namespace {
@@ -32,6 +33,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string err;
   bool load() {
@@ -42,8 +44,9 @@ struct NcclApi {
     CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
     CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
     AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
     GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) { err = "libnccl lacks a required symbol"; h = nullptr; return false; }
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !AllReduce || !GetErrorString) { err = "libnccl lacks a required symbol"; h = nullptr; return false; }
     return true;
   }
 };
@@ -107,6 +110,17 @@ struct hj3d_comm {
   bool   host_streamed[kSlots] = {false, false};
   hj3d_selection sel[kSlots] = {};
   void* h_pinned = nullptr;                      // world * kMaxRanges * 8 bytes
+  // hot-key probe replication (hot.cuh)
+  unsigned long long* d_sample[kSlots] = {nullptr, nullptr};      // [kHotSample] this rank's sample of the slot's relation
+  unsigned long long* d_sample_all[kSlots] = {nullptr, nullptr};  // [kHotSample] everybody's
+  void* d_hot_table[kSlots] = {nullptr, nullptr};                 // HotTable<KeyT>
+  void* hot_buf[kSlots] = {nullptr, nullptr};                     // local segment of the hot tuples' records
+  uint64_t hot_buf_records[kSlots] = {0, 0};
+  bool  hot_sampled[kSlots] = {false, false}, hot_selected[kSlots] = {false, false}, hot_on[kSlots] = {false, false};
+  uint32_t sample_m[kSlots] = {0, 0};
+  HotAnswers* d_ans[kSlots] = {nullptr, nullptr};                 // this rank's answers / the sum over all ranks
+  HotAnswers* d_ans_sum[kSlots] = {nullptr, nullptr};
+  cudaEvent_t ev_sample[kSlots] = {nullptr, nullptr}, ev_ans[kSlots] = {nullptr, nullptr};
 };
 
 namespace {
@@ -135,7 +149,12 @@ __global__ void k_xchg_starts(uint32_t n_ranges, uint32_t rpo_shift, uint32_t wo
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q > n_ranges) return;
   const uint32_t local = q & ((1u << rpo_shift) - 1u);
-  pstart[q] = ((unsigned long long)local * world + me) * cap_seg;
+  pstart[q] = q == n_ranges ? 0ull : ((unsigned long long)local * world + me) * cap_seg;   // [n_ranges]: the hot segment, a buffer of its own
+}
+
+__global__ void k_add_u32(uint32_t* __restrict__ acc, const uint32_t* __restrict__ x, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += x[i];
 }
 
 // owner side: segment table of my ranges from the gathered counts.  uniform: fixed regions; exact: tightly packed
@@ -169,6 +188,17 @@ int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsign
   peer.owner_shift = pl.rpo_shift;
   const Dir d = make_dir(pl.D, 0, pl.D);
   const PartFn pf = make_partfn(pl.width, 0, (uint32_t)pl.D);
+  if (cm->hot_on[slot]) {      // one more partition: the hot keys' tuples stay here
+    peer.hot_q = pl.n_ranges; peer.hot_base = cm->hot_buf[slot]; peer.hot_cap = cm->hot_buf_records[slot]; peer.hot_table = cm->d_hot_table[slot];
+    const uint32_t fan = pl.n_ranges + 1;
+    const size_t sm = part_smem_bytes<KeyT>(fan, TH, false);
+    auto kfn = k_part_scatter<HASH, false, false, TH, false, true, true>;
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kfn<<<nb, TH, sm, st>>>(src, nullptr, d, pf, fan, fan, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot], (Slot<KeyT>*)nullptr, peer);
+    ++c->launches;
+    CUDA_TRY(cudaGetLastError());
+    return HJ3D_OK;
+  }
   const size_t sm = part_smem_bytes<KeyT>(pl.n_ranges, TH, false);
   auto kfn = k_part_scatter<HASH, false, false, TH, false, true>;
   CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -219,7 +249,14 @@ int free_slot(hj3d_comm* cm, int slot) {
 int comm_alloc_state(hj3d_comm* cm) {
   CUDA_TRY(cudaSetDevice(cm->ctx->device));
   for (int s = 0; s < kSlots; ++s) {
-    CUDA_TRY(cudaMalloc((void**)&cm->d_cursor[s], kMaxRanges * 8));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_cursor[s], (kMaxRanges + 8) * 8));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_sample[s], kHotSample * 8));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_sample_all[s], kHotSample * 8));
+    CUDA_TRY(cudaMalloc(&cm->d_hot_table[s], sizeof(HotTable<uint64_t>)));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_ans[s], sizeof(HotAnswers)));
+    CUDA_TRY(cudaMalloc((void**)&cm->d_ans_sum[s], sizeof(HotAnswers)));
+    CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_sample[s], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_ans[s], cudaEventDisableTiming));
     CUDA_TRY(cudaMalloc((void**)&cm->d_all[s], (size_t)cm->world * kMaxRanges * 8));
     CUDA_TRY(cudaMalloc((void**)&cm->d_pstart[s], (kMaxRanges + 1) * 8));
     CUDA_TRY(cudaEventCreateWithFlags(&cm->ev_scatter[s], cudaEventDisableTiming));
@@ -230,6 +267,13 @@ int comm_alloc_state(hj3d_comm* cm) {
   CUDA_TRY(cudaMemset(cm->d_bar, 0, (1 + kMaxPeers) * 8));
   CUDA_TRY(cudaMallocHost(&cm->h_pinned, (size_t)(cm->world + 1) * kMaxRanges * 8));
   return HJ3D_OK;
+}
+
+template <int HASH> void launch_hot_select(hj3d_comm* cm, int slot, uint32_t m, cudaStream_t st) {
+  using KeyT = typename HashT<HASH>::key_t;
+  const int sm = kHotSample * (8 + 2);
+  cudaFuncSetAttribute(k_hot_select<HASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+  k_hot_select<HASH><<<1, 1024, sm, st>>>(cm->d_sample_all[slot], m, (HotTable<KeyT>*)cm->d_hot_table[slot]);
 }
 
 }  // namespace
@@ -315,6 +359,10 @@ int hj3d_comm_destroy(hj3d_comm* cm) {
     if (cm->ev_ready[s]) cudaEventDestroy(cm->ev_ready[s]);
     for (cudaEvent_t e : cm->chunk_ev[s]) cudaEventDestroy(e);
     cudaFree(cm->stage[s]);
+    cudaFree(cm->d_sample[s]); cudaFree(cm->d_sample_all[s]); cudaFree(cm->d_hot_table[s]); cudaFree(cm->hot_buf[s]);
+    cudaFree(cm->d_ans[s]); cudaFree(cm->d_ans_sum[s]);
+    if (cm->ev_sample[s]) cudaEventDestroy(cm->ev_sample[s]);
+    if (cm->ev_ans[s]) cudaEventDestroy(cm->ev_ans[s]);
   }
   if (cm->ev_fence) cudaEventDestroy(cm->ev_fence);
   if (cm->xstream) { cudaStreamSynchronize(cm->xstream); cudaStreamDestroy(cm->xstream); }
@@ -400,6 +448,88 @@ static int prepare_slot(hj3d_comm* cm, int slot, uint64_t n, hj3d_keyspec ks, ui
   cm->cap_seg[slot] = (min_recv / ((uint64_t)pl.rpo * cm->world)) & ~1ull;
   if (!cm->exact[slot] && cm->cap_seg[slot] < 2) return fail(HJ3D_ERR_INVALID, "receive buffer too small for the range x source regions");
   cm->sel[slot] = (sel && sel->op) ? *sel : hj3d_selection{0, 0, 0};
+  cm->hot_on[slot] = false;
+  if (flags & HJ3D_XCHG_HOT) {
+    if (flags & HJ3D_XCHG_EXACT) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT and HJ3D_XCHG_EXACT exclude each other");
+    if (!cm->hot_sampled[slot]) return fail(HJ3D_ERR_INVALID, "HJ3D_XCHG_HOT needs hj3d_exchange_hot_sample on this slot first");
+    if (pl.n_ranges >= kMaxRanges) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT needs fewer than 1024 bucket ranges");
+    cm->hot_on[slot] = true;
+  }
+  return HJ3D_OK;
+}
+
+// hot set of a slot: every rank runs k_hot_select on the same gathered sample (single process: gathered here)
+static int hot_select(hj3d_comm* cm, int slot) {
+  hj3d_ctx* c = cm->ctx;
+  const uint32_t m_r = cm->sample_m[slot];
+  uint32_t m = m_r * (uint32_t)cm->world;
+  if (!cm->nc) {
+    m = 0;
+    for (hj3d_comm* o : cm->group->ranks) {
+      if (!o) continue;
+      if (!o->hot_sampled[slot] || o->sample_m[slot] != m_r) return fail(HJ3D_ERR_INVALID, "every rank of the group must call hj3d_exchange_hot_sample before the first hj3d_exchange_begin");
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, o->ev_sample[slot], 0));
+      CUDA_TRY(cudaMemcpyAsync(cm->d_sample_all[slot] + (size_t)o->rank * m_r, o->d_sample[slot], (size_t)m_r * 8, cudaMemcpyDefault, c->stream));
+      m += m_r;
+    }
+  }
+  switch (cm->ks[slot].hash_id) {
+    case HJ3D_HASH_MURMUR32: launch_hot_select<HJ3D_HASH_MURMUR32>(cm, slot, m, c->stream); break;
+    case HJ3D_HASH_MURMUR64: launch_hot_select<HJ3D_HASH_MURMUR64>(cm, slot, m, c->stream); break;
+    default:                 launch_hot_select<HJ3D_HASH_MURMUR64_SEXT32>(cm, slot, m, c->stream); break;
+  }
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  cm->hot_selected[slot] = true;
+  return HJ3D_OK;
+}
+
+// Sample the slot's relation for hot keys (collective; before hj3d_exchange_begin(.., HJ3D_XCHG_HOT)).
+int hj3d_exchange_hot_sample(hj3d_comm* cm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks) {
+  if (!cm || slot < 0 || slot >= kSlots) return fail(HJ3D_ERR_INVALID, "bad exchange arguments");
+  if (n && !d_tuples) return fail(HJ3D_ERR_INVALID, "d_tuples == NULL");
+  HJ_TRY(check_keyspec(ks));
+  hj3d_ctx* c = cm->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint32_t m_r = (uint32_t)kHotSample / (uint32_t)cm->world;
+  const Src src = make_src(d_tuples, n, ks, nullptr);
+  if (ks.key_bytes == 8) k_hot_sample<uint64_t><<<blocks_for(m_r, 256), 256, 0, c->stream>>>(src, m_r, cm->d_sample[slot]);
+  else                   k_hot_sample<uint32_t><<<blocks_for(m_r, 256), 256, 0, c->stream>>>(src, m_r, cm->d_sample[slot]);
+  ++c->launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(cm->ev_sample[slot], c->stream));
+  cm->sample_m[slot] = m_r; cm->ks[slot] = ks;
+  cm->hot_sampled[slot] = true; cm->hot_selected[slot] = false;
+  if (cm->nc) {
+    NCCL_TRY(nccl().AllGather(cm->d_sample[slot], cm->d_sample_all[slot], m_r, ncclUint64, cm->nc, c->stream));
+    HJ_TRY(hot_select(cm, slot));
+  }
+  return HJ3D_OK;
+}
+
+// this rank's answers buffer (engine.cu fills it), and the all-reduce of the answers
+void* hj3d_comm_hot_ans_buffer(hj3d_comm* cm, int slot) { return cm->d_ans[slot]; }
+int hj3d_comm_hot_reduce_begin(hj3d_comm* cm, int slot) {
+  hj3d_ctx* c = cm->ctx;
+  constexpr size_t n32 = sizeof(HotAnswers) / 4;
+  if (cm->nc) NCCL_TRY(nccl().AllReduce(cm->d_ans[slot], cm->d_ans_sum[slot], n32, ncclUint32, ncclSum, cm->nc, c->stream));
+  else CUDA_TRY(cudaEventRecord(cm->ev_ans[slot], c->stream));
+  return HJ3D_OK;
+}
+int hj3d_comm_hot_reduce_end(hj3d_comm* cm, int slot, const void** d_sum) {
+  hj3d_ctx* c = cm->ctx;
+  constexpr uint32_t n32 = (uint32_t)(sizeof(HotAnswers) / 4);
+  if (!cm->nc) {
+    CUDA_TRY(cudaMemsetAsync(cm->d_ans_sum[slot], 0, sizeof(HotAnswers), c->stream));
+    for (hj3d_comm* o : cm->group->ranks) {
+      if (!o) continue;
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, o->ev_ans[slot], 0));
+      k_add_u32<<<blocks_for(n32, 256), 256, 0, c->stream>>>((uint32_t*)cm->d_ans_sum[slot], (const uint32_t*)o->d_ans[slot], n32);
+      ++c->launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
+  *d_sum = cm->d_ans_sum[slot];
   return HJ3D_OK;
 }
 
@@ -426,8 +556,18 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
   const ExchangePlan& pl = cm->plan[slot];
   const Src src = slot_src(cm, slot, d_tuples, n);
   cm->host_streamed[slot] = false;
+  if (cm->hot_on[slot]) {
+    if (flags & HJ3D_XCHG_MORE) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT cannot be streamed");
+    if (cm->hot_buf_records[slot] < n) {            // worst case: every local tuple is hot
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      cudaFree(cm->hot_buf[slot]); cm->hot_buf[slot] = nullptr; cm->hot_buf_records[slot] = 0;
+      HJ_TRY(raw_alloc(&cm->hot_buf[slot], (n ? n : 1) * (size_t)(ks.key_bytes == 8 ? 16 : 8)));
+      cm->hot_buf_records[slot] = n ? n : 1;
+    }
+    if (!cm->hot_selected[slot]) HJ_TRY(hot_select(cm, slot));
+  }
   PhaseTimer pt(c, PH_PARTITION);
-  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, (kMaxRanges + 8) * 8, c->stream));
   int rc = HJ3D_OK;
   if (!cm->exact[slot]) {
     k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, c->stream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
@@ -455,7 +595,7 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
 int hj3d_exchange_begin_host(hj3d_comm* cm, int slot, const void* h_tuples, uint64_t n, hj3d_keyspec ks, uint64_t D, uint32_t rowid_base,
                              uint32_t flags, const hj3d_selection* sel) {
   if (n && !h_tuples) return fail(HJ3D_ERR_INVALID, "h_tuples == NULL");
-  if (flags & (HJ3D_XCHG_EXACT | HJ3D_XCHG_MORE)) return fail(HJ3D_ERR_UNSUPPORTED, "hj3d_exchange_begin_host streams the slice once: no HJ3D_XCHG_EXACT / _MORE");
+  if (flags & (HJ3D_XCHG_EXACT | HJ3D_XCHG_MORE | HJ3D_XCHG_HOT)) return fail(HJ3D_ERR_UNSUPPORTED, "hj3d_exchange_begin_host streams the slice once: no HJ3D_XCHG_EXACT / _MORE / _HOT");
   HJ_TRY(prepare_slot(cm, slot, n, ks, D, flags, sel));
   if ((uint64_t)rowid_base + n > 0xFFFFFFFFull) return fail(HJ3D_ERR_UNSUPPORTED, "row ids past 2^32");
   hj3d_ctx* c = cm->ctx;
@@ -480,7 +620,7 @@ int hj3d_exchange_begin_host(hj3d_comm* cm, int slot, const void* h_tuples, uint
   CUDA_TRY(cudaEventRecord(cm->ev_fence, c->stream));
   CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, cm->ev_fence, 0));
   CUDA_TRY(cudaStreamWaitEvent(cm->xstream, cm->ev_fence, 0));
-  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, cm->xstream));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, (kMaxRanges + 8) * 8, cm->xstream));
   k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, cm->xstream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
   ++c->launches;
   for (size_t i = 0; i < n_chunks; ++i) {
@@ -539,7 +679,7 @@ static int exact_second_pass(hj3d_comm* cm, int slot, const void* d_tuples, uint
   if (worst > min_recv) return fail(HJ3D_ERR_NOMEM, "receive buffer too small for the exact exchange (a rank would receive " + std::to_string(worst) + " records)");
   h_ps[pl.n_ranges] = 0;
   CUDA_TRY(cudaMemcpyAsync(cm->d_pstart[slot], h_ps, ((size_t)pl.n_ranges + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, kMaxRanges * 8, c->stream));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, (kMaxRanges + 8) * 8, c->stream));
   const int rc = scatter_by_hash(cm, slot, slot_src(cm, slot, d_tuples, cm->n_local[slot]), rowid_base, ~0ull);
   if (rc < 0) return rc;
   CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
@@ -602,6 +742,13 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
       if (s == cm->rank) mine += cnt;
     }
   parts->n_total = recv; parts->n_sent_remote = sent; parts->n_local_selected = mine; parts->overflow = overflow;
+  if (cm->hot_on[slot]) {
+    const uint64_t hot = h_all[(size_t)cm->rank * kMaxRanges + pl.n_ranges];       // my own count of the extra partition
+    parts->hot_recs = cm->hot_buf[slot]; parts->hot_count = hot; parts->hot_table = cm->d_hot_table[slot];
+    parts->comm = cm; parts->slot = slot; parts->hot_mode = -1;
+    parts->n_local_selected += hot;
+    cm->hot_sampled[slot] = false;                   // a sample serves one exchange
+  }
   cm->pending[slot] = false;
   *out = parts.release();
   return overflow ? HJ3D_OVERFLOW : HJ3D_OK;

@@ -17,6 +17,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "hot_set.cuh"
 
 namespace hj3d {
 
@@ -137,10 +138,15 @@ template <class KeyT> inline size_t part_smem_bytes(uint32_t fan, int threads, b
 // PEER (multi-GPU exchange, exchange.cu): partition q belongs to owner q >> peer.owner_shift and its region lives in THAT
 // GPU's receive buffer peer.base[owner] (a peer-mapped pointer: the stores below travel over NVLink), at the offset
 // part_start[q]; `out` is unused.  The level-1 partition pass and the all-to-all are one kernel.
+// HOT (with PEER; hot.cuh): tuples whose key is in the hot set are not sent to the owner of their bucket range; they form
+// one more partition, peer.hot_q = the number of ranges, which stays in this GPU's own memory (peer.hot_base).
 constexpr int kMaxPeers = 16;
-struct PeerOut { void* base[kMaxPeers]; uint32_t owner_shift; };
+struct PeerOut {
+  void* base[kMaxPeers]; uint32_t owner_shift;
+  uint32_t hot_q; void* hot_base; unsigned long long hot_cap; const void* hot_table;   // HOT only
+};
 
-template <int HASH, bool LEFTID, bool RECS, int THREADS, bool RANK_MATCH, bool PEER = false>
+template <int HASH, bool LEFTID, bool RECS, int THREADS, bool RANK_MATCH, bool PEER = false, bool HOT = false>
 __global__ void __launch_bounds__(THREADS, THREADS <= 512 ? HJ3D_PART_MINBLOCKS : 1)
 k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint32_t n_parts, uint32_t fan,
                uint32_t rowid_base, unsigned long long cap,
@@ -160,10 +166,15 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   uint16_t*           pid  = reinterpret_cast<uint16_t*>(whist + (RANK_MATCH ? WARPS * fpad : 0));
   __shared__ uint32_t sm_scan[33];
   __shared__ uint32_t sm_q0;
+  __shared__ HotEntry<KeyT> sm_hot[HOT ? kHotSlots : 1];
   const uint32_t warp = threadIdx.x >> 5;
 
   uint64_t t0; uint32_t tn;
   block_tile<TILE>(tilemap, s.n, t0, tn);
+  if (HOT) {   // the hot set into shared memory (visible after the barrier below)
+    const HotTable<KeyT>* ht = reinterpret_cast<const HotTable<KeyT>*>(peer.hot_table);
+    for (uint32_t p = threadIdx.x; p < (uint32_t)kHotSlots; p += THREADS) sm_hot[p] = ht->slot[p];
+  }
   if (RANK_MATCH) { for (uint32_t p = threadIdx.x; p < WARPS * fpad; p += THREADS) whist[p] = 0; }
   else            { for (uint32_t p = threadIdx.x; p < fan; p += THREADS) hist[p] = 0; }
 
@@ -256,7 +267,8 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
     }
   }
   };
-  if (d.is_pow2 && pf.is_pow2) rank_all([&](KeyT k) { const uint32_t b = (HashT<HASH>::hash_lo32(k) & d.pow2_mask) - pf.lo; return b < pf.nl ? b >> pf.shift : 0xFFFFFFFFu; });
+  if (HOT)                     rank_all([&](KeyT k) { return hot_find(sm_hot, k, HashT<HASH>::hash_lo32(k)) >= 0 ? peer.hot_q : pf(HashT<HASH>::bucket(k, d)); });
+  else if (d.is_pow2 && pf.is_pow2) rank_all([&](KeyT k) { const uint32_t b = (HashT<HASH>::hash_lo32(k) & d.pow2_mask) - pf.lo; return b < pf.nl ? b >> pf.shift : 0xFFFFFFFFu; });
   else                         rank_all([&](KeyT k) { return pf(HashT<HASH>::bucket(k, d)); });
   __syncthreads();
   if (RANK_MATCH) {  // per partition: warp counts -> exclusive prefix over warps (each warp's base), total -> hist
@@ -292,7 +304,8 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
         const unsigned long long g = v[k] ? atomicAdd(&cursor[q0 + a + k], (unsigned long long)v[k]) : 0ull;
         loff[a + k] = ex;
         dst[a + k] = part_start[q0 + a + k] + g - ex;
-        const unsigned long long cap_p = cap ? cap : part_start[q0 + a + k + 1] - part_start[q0 + a + k];   // cap == 0: planned regions
+        const unsigned long long cap_p = (HOT && q0 + a + k == peer.hot_q) ? peer.hot_cap
+                                         : cap ? cap : part_start[q0 + a + k + 1] - part_start[q0 + a + k];   // cap == 0: planned regions
         const unsigned long long room = g < cap_p ? cap_p - g : 0ull;         // records of this run that still fit
         klim[a + k] = room >= (unsigned long long)v[k] ? 0xFFFFFFFFu : ex + (uint32_t)room;
       }
@@ -316,7 +329,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   // (a 32-bit index variant of this loop with a no-overflow fast path measured 0.5 ms SLOWER per 2^30 records)
   for (uint32_t k = threadIdx.x; k < kept; k += THREADS) {
     const uint32_t lp = pid[k];
-    SlotT* o = PEER ? reinterpret_cast<SlotT*>(peer.base[(q0 + lp) >> peer.owner_shift]) : out;
+    SlotT* o = PEER ? reinterpret_cast<SlotT*>((HOT && q0 + lp == peer.hot_q) ? peer.hot_base : peer.base[(q0 + lp) >> peer.owner_shift]) : out;
     if (k < klim[lp]) o[dst[lp] + k] = tile[k];
   }
 }

@@ -60,6 +60,70 @@ __device__ __forceinline__ void load_probe(const Src& s, uint64_t i, KeyT& key, 
   }
 }
 
+// One probe of a non-empty bucket of the chaining table: sp[0 .. n) are the bucket's slots.  nm = result tuples,
+// first = row of the first one in chain order, cmps += comparisons (algebra.hh:644-657).  Shared by the probe kernels
+// and the hot-key answers (hot.cuh).
+template <class KeyT, bool UNIQUE>
+__device__ __forceinline__ void chain_walk(const Slot<KeyT>* sp, uint32_t n, KeyT key, uint32_t& nm, uint32_t& first, uint32_t& cmps) {
+  if (!UNIQUE) {
+    uint32_t m = 0, f = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+      const Slot<KeyT> sl = sp[k];
+      if (sl.key == key) { if (m == 0) f = sl.rowid; ++m; }
+    }
+    nm = m; first = f;
+    cmps += n;                                        // whole chain is walked (algebra.hh:644-657)
+  } else if (n <= kOrderedMax) {
+    uint32_t k = 0;                                   // chain order: stop at the first match (algebra.hh:653-655)
+    for (; k < n; ++k) {
+      const Slot<KeyT> sl = sp[k];
+      if (sl.key == key) { nm = 1; first = sl.rowid; break; }
+    }
+    cmps += k < n ? k + 1 : n;
+  } else {
+    // unordered long bucket: first match in chain order [oldest, newest, .., second oldest] from row ids
+    uint32_t min_row = 0xFFFFFFFFu, best = 0; bool any = false, min_is_match = false;
+    for (uint32_t k = 0; k < n; ++k) {
+      const Slot<KeyT> sl = sp[k];
+      const bool hit = sl.key == key;
+      if (sl.rowid < min_row) { min_row = sl.rowid; min_is_match = hit; }
+      if (hit && (!any || sl.rowid > best)) { best = sl.rowid; any = true; }
+    }
+    if (!any) { cmps += n; }
+    else if (min_is_match) { cmps += 1; nm = 1; first = min_row; }
+    else {
+      uint32_t rank = 0;                              // #tuples of the bucket inserted before `best`
+      for (uint32_t k = 0; k < n; ++k) rank += sp[k].rowid < best;
+      cmps += n - rank + 1; nm = 1; first = best;
+    }
+  }
+}
+
+// One probe of a non-empty bucket of the nested table: gp[0 .. dk) are the bucket's groups (the main chain).  hit / g
+// (index inside the bucket) / frow (first row of the group), cmps += comparisons (ht_nested.hh:368-381).
+template <class KeyT>
+__device__ __forceinline__ void group_walk(const Group<KeyT>* gp, uint32_t dk, KeyT key, bool& hit, uint32_t& g, uint32_t& frow, uint32_t& cmps) {
+  if (dk <= kOrderedMax) {
+    uint32_t k = 0;                                    // first-appearance order: the walk of ht_nested.hh:371-379
+    for (; k < dk; ++k) {
+      const Group<KeyT> gr = gp[k];
+      if (gr.key == key) { hit = true; g = k; frow = gr.first_row; break; }
+    }
+    cmps += k < dk ? k + 1 : dk;
+  } else {
+    uint32_t my_first = 0, my_g = 0; bool found = false;
+    for (uint32_t k = 0; k < dk && !found; ++k) {
+      const Group<KeyT> gr = gp[k];
+      if (gr.key == key) { found = true; my_first = gr.first_row; my_g = k; }
+    }
+    if (!found) { cmps += dk; return; }
+    uint32_t before = 0;                               // groups whose first tuple was inserted earlier
+    for (uint32_t k = 0; k < dk; ++k) before += gp[k].first_row < my_first;
+    cmps += before + 1;
+    hit = true; g = my_g; frow = my_first;
+  }
+}
+
 // ---- one tile of chaining probes ----------------------------------------------------------------------
 // offp[b] .. offp[b+1] (minus slot_base) delimit bucket b's slots in slotp; both may live in shared or
 // global memory (the address space is known at every inlined call site).
@@ -91,39 +155,7 @@ __device__ __forceinline__ void probe_chaining_tile(const Src& s, const Dir& d, 
   for (int j = 0; j < ITEMS; ++j) {
     const uint32_t n = len[j];
     if (n == 0) continue;                               // empty bucket: no comparison (algebra.hh:640-643)
-    const Slot<KeyT>* sp = slotp + lo[j];
-    if (!UNIQUE) {
-      uint32_t m = 0, f = 0;
-      for (uint32_t k = 0; k < n; ++k) {
-        const Slot<KeyT> sl = sp[k];
-        if (sl.key == key[j]) { if (m == 0) f = sl.rowid; ++m; }
-      }
-      nm[j] = m; first[j] = f;
-      cmps += n;                                        // whole chain is walked (algebra.hh:644-657)
-    } else if (n <= kOrderedMax) {
-      uint32_t k = 0;                                   // chain order: stop at the first match (algebra.hh:653-655)
-      for (; k < n; ++k) {
-        const Slot<KeyT> sl = sp[k];
-        if (sl.key == key[j]) { nm[j] = 1; first[j] = sl.rowid; break; }
-      }
-      cmps += k < n ? k + 1 : n;
-    } else {
-      // unordered long bucket: first match in chain order [oldest, newest, .., second oldest] from row ids
-      uint32_t min_row = 0xFFFFFFFFu, best = 0; bool any = false, min_is_match = false;
-      for (uint32_t k = 0; k < n; ++k) {
-        const Slot<KeyT> sl = sp[k];
-        const bool hit = sl.key == key[j];
-        if (sl.rowid < min_row) { min_row = sl.rowid; min_is_match = hit; }
-        if (hit && (!any || sl.rowid > best)) { best = sl.rowid; any = true; }
-      }
-      if (!any) { cmps += n; }
-      else if (min_is_match) { cmps += 1; nm[j] = 1; first[j] = min_row; }
-      else {
-        uint32_t rank = 0;                              // #tuples of the bucket inserted before `best`
-        for (uint32_t k = 0; k < n; ++k) rank += sp[k].rowid < best;
-        cmps += n - rank + 1; nm[j] = 1; first[j] = best;
-      }
-    }
+    chain_walk<KeyT, UNIQUE>(slotp + lo[j], n, key[j], nm[j], first[j], cmps);
     mine += nm[j];
   }
   acc.matches += mine;
@@ -178,26 +210,9 @@ __device__ __forceinline__ void probe_nested_tile(const Src& s, const Dir& d, ui
     if (b >= n_buckets) continue;
     const uint32_t o0 = offp[b], dk = offp[b + 1] - o0;
     if (dk == 0) continue;                               // empty bucket: {nullptr, 0} (ht_nested.hh:372)
-    const Group<KeyT>* gp = grp + (o0 - group_base);
-    if (dk <= kOrderedMax) {
-      uint32_t k = 0;                                    // first-appearance order: the walk of ht_nested.hh:371-379
-      for (; k < dk; ++k) {
-        const Group<KeyT> g = gp[k];
-        if (g.key == key) { hit[j] = true; gref[j] = o0 + k; frow[j] = g.first_row; break; }
-      }
-      cmps += k < dk ? k + 1 : dk;
-    } else {
-      uint32_t my_first = 0, my_g = 0; bool found = false;
-      for (uint32_t k = 0; k < dk && !found; ++k) {
-        const Group<KeyT> g = gp[k];
-        if (g.key == key) { found = true; my_first = g.first_row; my_g = o0 + k; }
-      }
-      if (!found) { cmps += dk; continue; }
-      uint32_t before = 0;                               // groups whose first tuple was inserted earlier
-      for (uint32_t k = 0; k < dk; ++k) before += gp[k].first_row < my_first;
-      cmps += before + 1;
-      hit[j] = true; gref[j] = my_g; frow[j] = my_first;
-    }
+    uint32_t g = 0;
+    group_walk<KeyT>(grp + (o0 - group_base), dk, key, hit[j], g, frow[j], cmps);
+    if (hit[j]) gref[j] = o0 + g;
     mine += hit[j];
   }
   acc.matches += mine;

@@ -284,6 +284,15 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
                             * A chunk is partitioned while the next one is still being uploaded; not with HJ3D_XCHG_EXACT. */
 #define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256; 128 with more than one rank) */
 #define HJ3D_XOPT_MIN_RANGE_WIDTH 2 /* smallest range width in buckets (default 16384: a multiple of every fine-partition width) */
+#define HJ3D_XCHG_HOT   4u /* hot-key probe replication for a skewed PROBE side (Zipf foreign keys): tuples of the (at most 64)
+                            * most frequent keys are not sent to the owner of their bucket but stay on the GPU that read them;
+                            * once the tables are built every rank learns the owners' answers for the hot keys (one small
+                            * all-reduce) and joins its hot tuples locally.  Same results and counters, no owner serialises, and
+                            * the remaining tuples fit the uniform regions again (no HJ3D_XCHG_EXACT pass).  Call order:
+                            *   hj3d_exchange_hot_sample (every rank) -> hj3d_exchange_begin(.., HJ3D_XCHG_HOT) / _end
+                            *   -> build the table -> hj3d_parts_hot_answers (every rank) -> hj3d_probe_parts (mode 0, 1 or 3).
+                            * Hot keys with more than 8 build partners are refused (HJ3D_ERR_UNSUPPORTED from hj3d_probe_parts):
+                            * the feature is for foreign keys probing a (nearly) unique build side. */
 typedef struct hj3d_comm  hj3d_comm;
 typedef struct hj3d_parts hj3d_parts;
 int hj3d_comm_unique_id(void* id128);
@@ -304,6 +313,8 @@ int hj3d_exchange_begin_select(hj3d_comm* comm, int slot, const void* d_tuples, 
 int hj3d_parts_selected(hj3d_parts* parts, uint64_t* n_local_selected);
 int hj3d_exchange_begin(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks, uint64_t num_buckets,
                         uint32_t rowid_base, uint32_t flags);
+/* hot-key replication, step 1 (collective): sample the slot's relation; the ranks agree on the hot set on the device */
+int hj3d_exchange_hot_sample(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, hj3d_keyspec ks);
 /* next chunk of the local slice after a hj3d_exchange_begin(.., HJ3D_XCHG_MORE); rowid_base = global row id of its first tuple */
 int hj3d_exchange_append(hj3d_comm* comm, int slot, const void* d_tuples, uint64_t n, uint32_t rowid_base, uint32_t flags);
 /* The local slice is in HOST memory (pinned, for the overlap): it is uploaded in chunks of HJ3D_OPT_HOST_CHUNK_BYTES on a copy
@@ -323,6 +334,11 @@ int hj3d_parts_destroy(hj3d_parts* parts);
 int hj3d_table_build_parts(hj3d_ctx* ctx, hj3d_table* t, hj3d_parts* parts);
 int hj3d_probe_parts(hj3d_ctx* ctx, hj3d_table* t, hj3d_parts* parts, int mode, uint32_t flags, uint32_t* d_out_pairs, uint64_t out_cap,
                      hj3d_counters* probe_out, hj3d_counters* unnest_out);
+
+/* hot-key replication, step 3 (collective, after the table is built): what a probe with each hot key finds, from its owner */
+int hj3d_parts_hot_answers(hj3d_ctx* ctx, hj3d_table* t, hj3d_parts* probe_parts, int mode);
+/* number of tuples of this rank's slice that stayed local as hot-key tuples */
+int hj3d_parts_hot(hj3d_parts* parts, uint64_t* n_hot_records);
 
 /* Lower-level pieces (kept: callers that move the records themselves, e.g. over another transport).
  * owner(tuple) = bucket(tuple) / ceil(num_buckets / n_owners): contiguous bucket ranges.  Writes (key, global row id) pairs

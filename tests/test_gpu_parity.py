@@ -539,3 +539,89 @@ def test_exchange_and_sharded_join_in_one_process(pkg, oracle, world, host):
             cm.destroy()
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_hot_key_probe_replication(pkg, oracle, world):
+    """Skewed foreign keys (Zipf): hj3d_exchange_hot_sample -> hj3d_exchange_begin(HJ3D_XCHG_HOT): tuples of the most frequent
+    keys stay on the GPU that read them, the owners' answers for those keys are all-reduced (hj3d_parts_hot_answers) and the
+    hot tuples are joined locally.  Counters, statistics and the result multiset equal the unsharded reference result;
+    the ranks' loads even out and the uniform exchange regions do not overflow."""
+    import torch
+    import ctypes as C
+    lib = pkg.capi.load()
+    rng = np.random.default_rng(500 + world)
+    stream = torch.cuda.current_stream().cuda_stream
+    nR, nS, D = 50000, 400000, 1 << 16
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+    fk = (rng.zipf(1.2, nS).astype(np.uint64) - 1) % np.uint64(nR)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.permutation(fk.astype(np.uint32))
+    # a few build-side duplicates of the hottest key (non-unique walk) and a hot key without a partner
+    top = np.bincount(S[:, 1]).argmax()
+    R[:3, 0] = top
+    S[S[:, 1] == 1, 1] = nR + 7
+    ctxs = [pkg.Context(0, stream=stream) for _ in range(world)]
+    for c in ctxs:
+        c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0); c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 8192)
+        c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 8192); c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
+    comms = pkg.Comm.local(ctxs)
+    for cm in comms:
+        cm.set_option(pkg.capi.XOPT_MIN_RANGE_WIDTH, 1024)
+        cm.set_option(pkg.capi.XOPT_TARGET_RANGES, 64)
+    ksR, ksS = KSg(pkg, 12, 0), KSg(pkg, 12, 4)
+    dR, dS = to_dev(R).view(-1, 12), to_dev(S).view(-1, 12)
+    sl = lambda n, r: (r * n // world, (r + 1) * n // world)
+    for mode in (1, 0, 3):
+        o = oracle_plan(oracle, pyo, mode, R, pyo.KeySpec(12, 0), D, S, pyo.KeySpec(12, 4))
+        for cm in comms:
+            cm.reserve(0, int(nR * 1.5 / world) + 70000, 4)
+            cm.reserve(1, int(nS * 1.3 / world) + 70000, 4)          # uniform regions: only possible without the hot keys
+        slices = []
+        for r, cm in enumerate(comms):
+            b0, b1 = sl(nR, r); p0, p1 = sl(nS, r)
+            tb, tp = dR[b0:b1].contiguous(), dS[p0:p1].contiguous()
+            slices.append((tb, b0, b1, tp, p0, p1))
+            cm.hot_sample(1, tp, p1 - p0, ksS)
+        for r, cm in enumerate(comms):
+            tb, b0, b1, tp, p0, p1 = slices[r]
+            cm.begin(0, tb, b1 - b0, ksR, D, b0)
+            cm.begin(1, tp, p1 - p0, ksS, D, p0, flags=pkg.capi.XCHG_HOT)
+        tabs, pps, n_hot, n_recv = [], [], 0, []
+        for r, cm in enumerate(comms):
+            tb, b0, b1, tp, p0, p1 = slices[r]
+            rc, pb = cm.end(0, tb, b0, nR); assert rc == 0
+            rc, pp = cm.end(1, tp, p0, nS); assert rc == 0, "uniform regions overflowed although the hot keys stayed local"
+            lo, hi = cm.shard(D)
+            t = ctxs[r].table(pkg.CHAINING if mode <= 1 else pkg.NESTED, D, shard=(lo, hi))
+            t.build_parts(pb); pb.destroy()
+            t.hot_answers(pp, mode)
+            tabs.append(t); pps.append(pp); n_hot += pp.hot(); n_recv.append(pp.info()["n_records"])
+        assert n_hot > nS // 5, "the hot keys carry a large share of a Zipf(1.2) relation"
+        assert n_hot + sum(n_recv) == nS
+        parts = (pkg.Stats * world)()
+        tot = {"matches": 0, "num_cmps": 0}
+        pairs = []
+        for r in range(world):
+            t, pp = tabs[r], pps[r]
+            _, c0, u0 = t.probe_parts(pp, mode, flags=pkg.F_CHECKSUM)
+            n_out = (u0 if mode == 3 else c0)["out_tuples"]
+            out = torch.zeros((max(n_out, 1), 2), dtype=torch.int32, device="cuda")
+            _, c1, u1 = t.probe_parts(pp, mode, flags=pkg.F_CHECKSUM, out=out, out_cap=n_out)
+            assert sub(c1) == sub(c0) and sub(u1) == sub(u0)
+            res = u1 if mode == 3 else c1
+            assert res["out_written"] == n_out
+            got = out[:n_out].cpu().numpy().view(np.uint32)
+            pairs.append(got)
+            tot["matches"] += c1["matches"]; tot["num_cmps"] += c1["num_cmps"]
+            parts[r] = pkg.Stats(**t.stats())
+            t.destroy(); pp.destroy()
+        what = f"hot world={world} mode={mode}"
+        merged = pkg.Stats()
+        lib.hj3d_stats_merge(parts, world, C.byref(merged))
+        assert merged.as_dict() == o["stats"], what
+        assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"], what
+        assert np.array_equal(sorted_pairs(np.concatenate(pairs)), sorted_pairs(o["pairs"])), what
+    for cm in comms:
+        cm.destroy()
+    for c in ctxs:
+        c.close()
