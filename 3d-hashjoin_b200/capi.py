@@ -25,7 +25,7 @@ OPT_PACKED_PROBE, OPT_PACKED_MIN_PROBE, OPT_PACKED_SLICE_BYTES = 21, 22, 23
 GEN_IOTA, GEN_PERMUTATION, GEN_UNIFORM, GEN_ZIPF, GEN_CONST = 0, 1, 2, 3, 4
 XCHG_EXACT, XCHG_MORE, XCHG_HOT = 1, 2, 4
 OPT_HOST_CHUNK_BYTES = 24
-XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH = 1, 2
+XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH, XOPT_MAX_RANGE_WIDTH, XOPT_THREADS = 1, 2, 3, 4
 
 # every symbol include/hj3d.h declares (tests check that the library exports all of them)
 SYMBOLS = [

@@ -78,7 +78,7 @@ struct hj3d_comm {
   int world = 1, rank = 0;
   ncclComm_t nc = nullptr;                       // multi-process mode
   std::shared_ptr<LocalGroup> group;             // single-process mode
-  int64_t target_ranges = 256, min_width = 16384;
+  int64_t target_ranges = 256, min_width = 16384, max_width = 1 << 21, xchg_threads = 0;
   // receive buffers of this rank and the peers' mapped views of them
   void*    recv[kSlots] = {nullptr, nullptr};
   uint64_t recv_records[kSlots] = {0, 0};
@@ -134,6 +134,10 @@ ExchangePlan make_plan(const hj3d_comm* cm, uint64_t D) {
   while (w < want) w <<= 1;
   uint64_t mw = 1; while ((int64_t)mw < cm->min_width) mw <<= 1;
   if (w < mw) w = mw;
+  // the local join continues at partition level 2 only if a range holds at most 1024 fine partitions (2048 buckets each for
+  // 8-byte slots of unique keys): wider ranges would be compacted and partitioned from scratch (engine.cu, plan_probe)
+  uint64_t xw = 1; while ((int64_t)(xw << 1) <= cm->max_width) xw <<= 1;
+  if (w > xw && xw >= mw) w = xw;
   while ((D + w - 1) / w > kMaxRanges) w <<= 1;
   p.width = (uint32_t)(w > 0x80000000ull ? 0x80000000ull : w);
   p.n_ranges = (uint32_t)((D + p.width - 1) / p.width);
@@ -173,13 +177,13 @@ __global__ void k_xchg_segments(const unsigned long long* __restrict__ all, uint
     }
 }
 
-template <int HASH>
-int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap, cudaStream_t st = nullptr) {
+// TH = block size: 512 (tiles of 8192 8-byte records, two blocks per SM) or 1024 (tiles of 16384: the sorted runs a tile
+// stores into one peer region are twice as long, which is what the NVLink store rate depends on; the default across GPUs)
+template <int HASH, int TH>
+int launch_scatter_t(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap, cudaStream_t st) {
   using KeyT = typename HashT<HASH>::key_t;
   hj3d_ctx* c = cm->ctx;
-  if (!st) st = c->stream;
   const ExchangePlan& pl = cm->plan[slot];
-  constexpr int TH = 512;
   const int kTile = TH * PartCfg<KeyT>::kItems;
   const uint32_t nb = blocks_for(src.n, kTile);
   if (!nb) return HJ3D_OK;
@@ -195,18 +199,24 @@ int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsign
     auto kfn = k_part_scatter<HASH, false, false, TH, false, true, true>;
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     kfn<<<nb, TH, sm, st>>>(src, nullptr, d, pf, fan, fan, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot], (Slot<KeyT>*)nullptr, peer);
-    ++c->launches;
-    CUDA_TRY(cudaGetLastError());
-    return HJ3D_OK;
+  } else {
+    const size_t sm = part_smem_bytes<KeyT>(pl.n_ranges, TH, false);
+    auto kfn = k_part_scatter<HASH, false, false, TH, false, true>;
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kfn<<<nb, TH, sm, st>>>(src, nullptr, d, pf, pl.n_ranges, pl.n_ranges, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot],
+                            (Slot<KeyT>*)nullptr, peer);
   }
-  const size_t sm = part_smem_bytes<KeyT>(pl.n_ranges, TH, false);
-  auto kfn = k_part_scatter<HASH, false, false, TH, false, true>;
-  CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  kfn<<<nb, TH, sm, st>>>(src, nullptr, d, pf, pl.n_ranges, pl.n_ranges, rowid_base, cap, cm->d_pstart[slot], cm->d_cursor[slot],
-                                 (Slot<KeyT>*)nullptr, peer);
   ++c->launches;
   CUDA_TRY(cudaGetLastError());
   return HJ3D_OK;
+}
+
+template <int HASH>
+int launch_scatter(hj3d_comm* cm, int slot, Src src, uint32_t rowid_base, unsigned long long cap, cudaStream_t st = nullptr) {
+  if (!st) st = cm->ctx->stream;
+  const int64_t th = cm->xchg_threads ? cm->xchg_threads : (cm->world > 1 ? 1024 : 512);   // measured at 2 GPUs: 4.55 vs 4.75 ms (128 ranges), 11.8 vs 12.8 ms (512)
+  if (th == 1024) return launch_scatter_t<HASH, 1024>(cm, slot, src, rowid_base, cap, st);
+  return launch_scatter_t<HASH, 512>(cm, slot, src, rowid_base, cap, st);
 }
 
 template <int HASH>
@@ -341,6 +351,8 @@ int hj3d_comm_set_option(hj3d_comm* cm, int opt, int64_t v) {
   switch (opt) {
     case HJ3D_XOPT_TARGET_RANGES: if (v >= 1 && v <= (int64_t)kMaxRanges) cm->target_ranges = v; break;
     case HJ3D_XOPT_MIN_RANGE_WIDTH: if (v >= 1) cm->min_width = v; break;
+    case HJ3D_XOPT_MAX_RANGE_WIDTH: if (v >= 1) cm->max_width = v; break;
+    case HJ3D_XOPT_THREADS: if (v == 0 || v == 512 || v == 1024) cm->xchg_threads = v; break;
     default: return fail(HJ3D_ERR_INVALID, "unknown comm option");
   }
   return HJ3D_OK;
@@ -452,7 +464,6 @@ static int prepare_slot(hj3d_comm* cm, int slot, uint64_t n, hj3d_keyspec ks, ui
   if (flags & HJ3D_XCHG_HOT) {
     if (flags & HJ3D_XCHG_EXACT) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT and HJ3D_XCHG_EXACT exclude each other");
     if (!cm->hot_sampled[slot]) return fail(HJ3D_ERR_INVALID, "HJ3D_XCHG_HOT needs hj3d_exchange_hot_sample on this slot first");
-    if (pl.n_ranges >= kMaxRanges) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT needs fewer than 1024 bucket ranges");
     cm->hot_on[slot] = true;
   }
   return HJ3D_OK;
@@ -743,7 +754,10 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
     }
   parts->n_total = recv; parts->n_sent_remote = sent; parts->n_local_selected = mine; parts->overflow = overflow;
   if (cm->hot_on[slot]) {
-    const uint64_t hot = h_all[(size_t)cm->rank * kMaxRanges + pl.n_ranges];       // my own count of the extra partition
+    unsigned long long* h_hot = h_all + (size_t)cm->world * kMaxRanges;             // my own count of the extra partition
+    CUDA_TRY(cudaMemcpyAsync(h_hot, cm->d_cursor[slot] + pl.n_ranges, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const uint64_t hot = *h_hot;
     parts->hot_recs = cm->hot_buf[slot]; parts->hot_count = hot; parts->hot_table = cm->d_hot_table[slot];
     parts->comm = cm; parts->slot = slot; parts->hot_mode = -1;
     parts->n_local_selected += hot;

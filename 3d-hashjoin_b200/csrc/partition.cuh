@@ -282,7 +282,7 @@ k_part_scatter(Src s, const uint2* __restrict__ tilemap, Dir d, PartFn pf, uint3
   }
   // exclusive scan of the tile histogram (fan <= 1024: entries threadIdx*k.. ) + one range reservation per partition
   {
-    constexpr int PER = (kMaxParts + THREADS - 1) / THREADS;
+    constexpr int PER = (kMaxParts + (HOT ? 1 : 0) + THREADS - 1) / THREADS;      // HOT: one partition past the 1024 ranges
     const uint32_t a = PER * threadIdx.x;
     uint32_t v[PER], sum = 0;
 #pragma unroll

@@ -329,14 +329,26 @@ def run_ours(args):
         comm = pkg.Comm.create(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
         if args.xranges:
             comm.set_option(pkg.capi.XOPT_TARGET_RANGES, args.xranges)
+        # a range must hold at most 1024 fine partitions of the table (2048 buckets each for a chaining table on unique keys, 1024 for
+        # a nested one) or the local join cannot continue at partition level 2
+        comm.set_option(pkg.capi.XOPT_MAX_RANGE_WIDTH, args.xmaxwidth or ((1 << 20) if kind_name == "nested" else (1 << 21)))
+        if args.xthreads:
+            comm.set_option(pkg.capi.XOPT_THREADS, args.xthreads)
         slack = 1.25 if args.zipf <= 0 else float(world)        # skew: one owner may receive most of a relation
+        # hot-key probe replication (--zipf with a uniform build side R, plans Csr / CsrUU / Nsr): the tuples of the hottest
+        # foreign keys never leave the GPU that read them, so the uniform single-pass exchange works again
+        hot = args.zipf > 0 and build_rel == "R" and mode != 2 and not args.no_hot and not args.exact_exchange
+        if hot:
+            slack = 2.5      # the keys below the 128 hottest still differ: room for ranges up to 2.5x the mean
         comm.reserve(0, int(nBg / world * slack) + (1 << 20), 4)
         comm.reserve(1, int(nPg / world * slack) + (1 << 20), 4)
         lo_, hi_ = comm.shard(D)
         table = ctx.table(kind, D, shard=(lo_, hi_))
     else:
         table = ctx.table(kind, D)
-    xflags = pkg.capi.XCHG_EXACT if (args.zipf > 0 or args.exact_exchange) else 0
+    if world == 1:
+        hot = False
+    xflags = pkg.capi.XCHG_EXACT if ((args.zipf > 0 and not hot) or args.exact_exchange) else 0
 
     def step(fl=None):
         fl = flags if fl is None else fl
@@ -344,14 +356,19 @@ def run_ours(args):
         if world > 1:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
+            if hot:
+                comm.hot_sample(1, P, nPl, ksP)
             comm.begin(0, B, nBl, ksB, D, rank * nBl, xflags)
-            comm.begin(1, P, nPl, ksP, D, rank * nPl, xflags)
+            comm.begin(1, P, nPl, ksP, D, rank * nPl, pkg.capi.XCHG_HOT if hot else xflags)
             rc0, pb = comm.end(0, B, rank * nBl, nBg)
             rc1, pp = comm.end(1, P, rank * nPl, nPg)
             ev[1].record()
             assert rc0 == 0 and rc1 == 0, "exchange region overflow (run with --exact-exchange)"
             table.build_parts(pb)
             tb = ctx.timings()
+            if hot:
+                table.hot_answers(pp, mode)
+                state["hot_tuples"] = pp.hot()
             rc, c, u = table.probe_parts(pp, mode, flags=fl, out=out, out_cap=cap_out)
             tp = ctx.timings()
             ev[2].record()
@@ -456,6 +473,12 @@ def run_ours(args):
         ms = float(t.item())
     out_total, cmps_total, launches = all_sum([res["out_tuples"], state["probe_counters"]["num_cmps"], launches])
     assert out_total == nS, f"join produced {out_total} tuples, expected |S| = {nS}"
+    per_rank = None
+    if dist is not None:      # per-rank share of the result and of the received probe side (skew: the owner of a hot key)
+        t = torch.tensor([res["out_tuples"], state.get("hot_tuples", 0), state["n_probe_local"]], dtype=torch.int64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [a.tolist() for a in allt]
     assert cmps_total == got_cmps
     value = (nR + nS) / (ms * 1e-3)
     peak, peak_src = peaks()
@@ -509,7 +532,7 @@ def run_ours(args):
     #   N > 1: every rank holds its slice of both relations in pinned host memory and streams it through the exchange
     #          (hj3d_exchange_begin_host): upload, NVLink exchange, build and probe overlap; wall clock, max over ranks
     e2e = None
-    if not args.no_e2e and not (world > 1 and xflags):
+    if not args.no_e2e and not (world > 1 and (xflags or hot)):
         try:
             hB = torch.empty((nBl, 3), dtype=torch.int32).pin_memory(); hB.copy_(B)
             hP = torch.empty((nPl, 3), dtype=torch.int32).pin_memory(); hP.copy_(P)
@@ -616,7 +639,11 @@ def run_ours(args):
         join_ms_ = state["xev"][1].elapsed_time(state["xev"][2])
         line["shuffle"] = {"bytes_sent_per_gpu": state["sent"], "exchange_ms": part_ms, "local_join_ms": join_ms_,
                            "bus_gbs_per_gpu": state["sent"] / (part_ms * 1e-3) / 1e9 if part_ms > 0 else None,
-                           "exact_two_pass": bool(xflags),
+                           "exact_two_pass": bool(xflags), "hot_key_replication": bool(hot),
+                           "hot_tuples_kept_local": sum(a[1] for a in per_rank),
+                           "out_tuples_per_rank": [a[0] for a in per_rank],
+                           "out_imbalance_max_over_mean": max(a[0] for a in per_rank) * world / max(1, sum(a[0] for a in per_rank)),
+                           "probe_records_received_per_rank": [a[2] for a in per_rank],
                            "note": "rank 0, last step.  exchange_ms = partition level 1 of both relations with peer stores into the owners' "
                                    "receive buffers + two count all-gathers (the only collectives); there is no separate all-to-all.  "
                                    "bus_gbs_per_gpu = bytes this GPU stored into other GPUs / exchange_ms (a lower bound on the link rate, "
@@ -822,6 +849,7 @@ def run_config5(args):
         comm = pkg.Comm.create(ctx, world, rank, bytes(idt.cpu().numpy().tobytes()))
     else:
         comm = pkg.Comm.create(ctx, 1, 0, None)
+    comm.set_option(pkg.capi.XOPT_MAX_RANGE_WIDTH, args.xmaxwidth or (1 << 20))      # nested table: 1024 fine partitions of 1024 buckets per range
     slack = 1.25 if args.zipf <= 0 else float(max(world, 1))
     comm.reserve(0, int(nR / world * slack) + (1 << 20), 4)
     comm.reserve(1, int(nL / world * 1.25) + (1 << 20), 4)
@@ -913,7 +941,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the other plans (N=1)")
     ap.add_argument("--no-unsharded-check", action="store_true", help="N>1: skip rank 0's unsharded join of the same data")
+    ap.add_argument("--no-hot", action="store_true", help="N>1 with --zipf: no hot-key probe replication (two-pass exact exchange instead)")
     ap.add_argument("--exact-exchange", action="store_true", help="N>1: two-pass exchange with exact regions (always on with --zipf)")
+    ap.add_argument("--xmaxwidth", type=int, default=0, help="N>1: largest bucket-range width of the exchange (default 2^21, nested tables 2^20)")
+    ap.add_argument("--xthreads", type=int, default=0, help="N>1: block size of the exchange kernel (512 | 1024; default 1024)")
     ap.add_argument("--xranges", type=int, default=0, help="N>1: coarse bucket ranges of the exchange (default: the engine's 256)")
     ap.add_argument("--zipf", type=float, default=0.0, help="skew of the foreign keys S.a (0 = uniform; config 4 uses 0.5 .. 1.5)")
     ap.add_argument("--checksum", action="store_true",

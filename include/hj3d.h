@@ -283,8 +283,11 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
 #define HJ3D_XCHG_MORE  2u /* streamed slice: further chunks follow through hj3d_exchange_append (the last one without this flag).
                             * A chunk is partitioned while the next one is still being uploaded; not with HJ3D_XCHG_EXACT. */
 #define HJ3D_XOPT_TARGET_RANGES   1 /* coarse bucket ranges over the whole directory (default 256; 128 with more than one rank) */
+#define HJ3D_XOPT_MAX_RANGE_WIDTH 3 /* largest range width in buckets (default 2^21 = 1024 fine partitions of a chaining table on unique keys; use 2^20
+                                     * for nested tables): the local join continues at partition level 2 only below 1024 fine partitions per range */
+#define HJ3D_XOPT_THREADS         4 /* block size of the exchange's partition kernel: 512, 1024, 0 = 1024 with more than one rank (default) */
 #define HJ3D_XOPT_MIN_RANGE_WIDTH 2 /* smallest range width in buckets (default 16384: a multiple of every fine-partition width) */
-#define HJ3D_XCHG_HOT   4u /* hot-key probe replication for a skewed PROBE side (Zipf foreign keys): tuples of the (at most 64)
+#define HJ3D_XCHG_HOT   4u /* hot-key probe replication for a skewed PROBE side (Zipf foreign keys): tuples of the (at most 128)
                             * most frequent keys are not sent to the owner of their bucket but stay on the GPU that read them;
                             * once the tables are built every rank learns the owners' answers for the hot keys (one small
                             * all-reduce) and joins its hot tuples locally.  Same results and counters, no owner serialises, and
