@@ -23,7 +23,7 @@ OPT_LEAN_PROBE = 18
 OPT_UNNEST_HOT_CAP, OPT_PART_SAMPLE = 19, 20
 OPT_PACKED_PROBE, OPT_PACKED_MIN_PROBE, OPT_PACKED_SLICE_BYTES = 21, 22, 23
 GEN_IOTA, GEN_PERMUTATION, GEN_UNIFORM, GEN_ZIPF, GEN_CONST = 0, 1, 2, 3, 4
-XCHG_EXACT, XCHG_MORE, XCHG_HOT = 1, 2, 4
+XCHG_EXACT, XCHG_MORE, XCHG_HOT, XCHG_ASYNC = 1, 2, 4, 8
 OPT_HOST_CHUNK_BYTES = 24
 XOPT_TARGET_RANGES, XOPT_MIN_RANGE_WIDTH, XOPT_MAX_RANGE_WIDTH, XOPT_THREADS = 1, 2, 3, 4
 

@@ -108,6 +108,7 @@ struct hj3d_comm {
   void*  stage[kSlots] = {nullptr, nullptr};
   size_t stage_bytes[kSlots] = {0, 0};
   bool   host_streamed[kSlots] = {false, false};
+  bool   async_on[kSlots] = {false, false};       // HJ3D_XCHG_ASYNC: the exchange runs on xstream, hj3d_exchange_end joins it
   hj3d_selection sel[kSlots] = {};
   void* h_pinned = nullptr;                      // world * kMaxRanges * 8 bytes
   // hot-key probe replication (hot.cuh)
@@ -567,23 +568,36 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
   const ExchangePlan& pl = cm->plan[slot];
   const Src src = slot_src(cm, slot, d_tuples, n);
   cm->host_streamed[slot] = false;
+  cm->async_on[slot] = (flags & HJ3D_XCHG_ASYNC) != 0;
+  if (cm->async_on[slot] && (flags & (HJ3D_XCHG_EXACT | HJ3D_XCHG_MORE))) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_ASYNC goes with the single-pass exchange only");
   if (cm->hot_on[slot]) {
     if (flags & HJ3D_XCHG_MORE) return fail(HJ3D_ERR_UNSUPPORTED, "HJ3D_XCHG_HOT cannot be streamed");
     if (cm->hot_buf_records[slot] < n) {            // worst case: every local tuple is hot
       CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (cm->xstream) CUDA_TRY(cudaStreamSynchronize(cm->xstream));
       cudaFree(cm->hot_buf[slot]); cm->hot_buf[slot] = nullptr; cm->hot_buf_records[slot] = 0;
       HJ_TRY(raw_alloc(&cm->hot_buf[slot], (n ? n : 1) * (size_t)(ks.key_bytes == 8 ? 16 : 8)));
       cm->hot_buf_records[slot] = n ? n : 1;
     }
     if (!cm->hot_selected[slot]) HJ_TRY(hot_select(cm, slot));
   }
-  PhaseTimer pt(c, PH_PARTITION);
-  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, (kMaxRanges + 8) * 8, c->stream));
+  // HJ3D_XCHG_ASYNC: everything below runs on the communicator's own stream, ordered after what the ctx stream holds now;
+  // the ctx stream is free for other work (building the table of the other relation) until hj3d_exchange_end joins it
+  cudaStream_t st = c->stream;
+  if (cm->async_on[slot]) {
+    if (!cm->xstream) CUDA_TRY(cudaStreamCreateWithFlags(&cm->xstream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventRecord(cm->ev_fence, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(cm->xstream, cm->ev_fence, 0));
+    st = cm->xstream;
+  }
+  std::unique_ptr<PhaseTimer> pt;                    // (the phase events live on the ctx stream)
+  if (!cm->async_on[slot]) pt.reset(new PhaseTimer(c, PH_PARTITION));
+  CUDA_TRY(cudaMemsetAsync(cm->d_cursor[slot], 0, (kMaxRanges + 8) * 8, st));
   int rc = HJ3D_OK;
   if (!cm->exact[slot]) {
-    k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, c->stream>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
+    k_xchg_starts<<<blocks_for(pl.n_ranges + 1, 256), 256, 0, st>>>(pl.n_ranges, pl.rpo_shift, cm->world, cm->rank, cm->cap_seg[slot], cm->d_pstart[slot]);
     ++c->launches;
-    rc = scatter_by_hash(cm, slot, src, rowid_base, cm->cap_seg[slot]);
+    rc = scatter_by_hash(cm, slot, src, rowid_base, cm->cap_seg[slot], st);
   } else {
     switch (ks.hash_id) {
       case HJ3D_HASH_MURMUR32: rc = launch_hist<HJ3D_HASH_MURMUR32>(cm, slot, src); break;
@@ -595,8 +609,9 @@ int hj3d_exchange_begin_select(hj3d_comm* cm, int slot, const void* d_tuples, ui
   cm->pending[slot] = true;
   cm->streaming[slot] = (flags & HJ3D_XCHG_MORE) != 0;
   if (cm->streaming[slot]) return HJ3D_OK;           // the counts leave with the last chunk
-  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], c->stream));
-  if (cm->nc) HJ_TRY(gather_counts(cm, slot));       // multi-process: enqueue the all-gather right behind the kernel
+  CUDA_TRY(cudaEventRecord(cm->ev_scatter[slot], st));
+  if (cm->nc) HJ_TRY(gather_counts(cm, slot, st));   // multi-process: enqueue the all-gather right behind the kernel
+  if (cm->async_on[slot]) CUDA_TRY(cudaEventRecord(cm->ev_ready[slot], st));
   return HJ3D_OK;
 }
 
@@ -712,6 +727,10 @@ int hj3d_exchange_end(hj3d_comm* cm, int slot, const void* d_tuples, uint32_t ro
     if (cm->n_chunks[slot]) CUDA_TRY(cudaEventSynchronize(cm->chunk_ev[slot][cm->n_chunks[slot] - 1]));
     CUDA_TRY(cudaStreamWaitEvent(c->stream, cm->ev_ready[slot], 0));
     cm->host_streamed[slot] = false;
+  }
+  if (cm->async_on[slot]) {
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, cm->ev_ready[slot], 0));
+    cm->async_on[slot] = false;
   }
   if (cm->streaming[slot]) {                         // ended without a final append: the chunks so far are the slice
     cm->streaming[slot] = false;

@@ -248,6 +248,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    if args.overlap:      # the ctx (and torch) work on a high-priority stream: the build's blocks go ahead of the exchange's
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=-1))
     ctx = pkg.Context(local, stream=torch.cuda.current_stream().cuda_stream)
     for o in args.opt:
         k, v = o.split("=")
@@ -350,7 +352,7 @@ def run_ours(args):
         hot = False
     xflags = pkg.capi.XCHG_EXACT if ((args.zipf > 0 and not hot) or args.exact_exchange) else 0
 
-    def step(fl=None):
+    def step(fl=None, overlap=False):
         fl = flags if fl is None else fl
         table.clear()
         if world > 1:
@@ -359,13 +361,22 @@ def run_ours(args):
             if hot:
                 comm.hot_sample(1, P, nPl, ksP)
             comm.begin(0, B, nBl, ksB, D, rank * nBl, xflags)
-            comm.begin(1, P, nPl, ksP, D, rank * nPl, pkg.capi.XCHG_HOT if hot else xflags)
-            rc0, pb = comm.end(0, B, rank * nBl, nBg)
-            rc1, pp = comm.end(1, P, rank * nPl, nPg)
-            ev[1].record()
+            if overlap and not xflags:
+                # the probe side's exchange runs on the communicator's (low priority) stream while this stream builds the table
+                comm.begin(1, P, nPl, ksP, D, rank * nPl, (pkg.capi.XCHG_HOT if hot else 0) | pkg.capi.XCHG_ASYNC)
+                rc0, pb = comm.end(0, B, rank * nBl, nBg)
+                table.build_parts(pb)
+                tb = ctx.timings()
+                rc1, pp = comm.end(1, P, rank * nPl, nPg)
+                ev[1].record()
+            else:
+                comm.begin(1, P, nPl, ksP, D, rank * nPl, pkg.capi.XCHG_HOT if hot else xflags)
+                rc0, pb = comm.end(0, B, rank * nBl, nBg)
+                rc1, pp = comm.end(1, P, rank * nPl, nPg)
+                ev[1].record()
+                table.build_parts(pb)
+                tb = ctx.timings()
             assert rc0 == 0 and rc1 == 0, "exchange region overflow (run with --exact-exchange)"
-            table.build_parts(pb)
-            tb = ctx.timings()
             if hot:
                 table.hot_answers(pp, mode)
                 state["hot_tuples"] = pp.hot()
@@ -447,7 +458,7 @@ def run_ours(args):
     if sampler:
         sampler.start()
     for _ in range(args.warmup):
-        step()
+        step(overlap=args.overlap)
     sync_all()
     launches0 = ctx.timings()["kernel_launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -457,7 +468,7 @@ def run_ours(args):
         sampler.t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        res = step()
+        res = step(overlap=args.overlap)
         probe_ms.append(state["probe"]["probe_ms"]); build_ms.append(state["build"]["total_ms"])
         l1_ms.append(state["probe"]["partition_l1_ms"])
     e1.record()
@@ -640,6 +651,7 @@ def run_ours(args):
         line["shuffle"] = {"bytes_sent_per_gpu": state["sent"], "exchange_ms": part_ms, "local_join_ms": join_ms_,
                            "bus_gbs_per_gpu": state["sent"] / (part_ms * 1e-3) / 1e9 if part_ms > 0 else None,
                            "exact_two_pass": bool(xflags), "hot_key_replication": bool(hot),
+                           "probe_exchange_overlaps_build": bool(args.overlap and not xflags),
                            "hot_tuples_kept_local": sum(a[1] for a in per_rank),
                            "out_tuples_per_rank": [a[0] for a in per_rank],
                            "out_imbalance_max_over_mean": max(a[0] for a in per_rank) * world / max(1, sum(a[0] for a in per_rank)),
@@ -944,6 +956,7 @@ def main():
     ap.add_argument("--no-hot", action="store_true", help="N>1 with --zipf: no hot-key probe replication (two-pass exact exchange instead)")
     ap.add_argument("--exact-exchange", action="store_true", help="N>1: two-pass exchange with exact regions (always on with --zipf)")
     ap.add_argument("--xmaxwidth", type=int, default=0, help="N>1: largest bucket-range width of the exchange (default 2^21, nested tables 2^20)")
+    ap.add_argument("--overlap", action="store_true", help="N>1: run the probe side's exchange on a second stream under the build")
     ap.add_argument("--xthreads", type=int, default=0, help="N>1: block size of the exchange kernel (512 | 1024; default 1024)")
     ap.add_argument("--xranges", type=int, default=0, help="N>1: coarse bucket ranges of the exchange (default: the engine's 256)")
     ap.add_argument("--zipf", type=float, default=0.0, help="skew of the foreign keys S.a (0 = uniform; config 4 uses 0.5 .. 1.5)")

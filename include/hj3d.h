@@ -296,6 +296,8 @@ int hj3d_join_host(hj3d_ctx* ctx, int mode,
                             *   -> build the table -> hj3d_parts_hot_answers (every rank) -> hj3d_probe_parts (mode 0, 1 or 3).
                             * Hot keys with more than 8 build partners are refused (HJ3D_ERR_UNSUPPORTED from hj3d_probe_parts):
                             * the feature is for foreign keys probing a (nearly) unique build side. */
+#define HJ3D_XCHG_ASYNC 8u /* run this exchange on a stream of the communicator: work queued on the ctx's stream until
+                            * hj3d_exchange_end (building the table from the other relation) overlaps it */
 typedef struct hj3d_comm  hj3d_comm;
 typedef struct hj3d_parts hj3d_parts;
 int hj3d_comm_unique_id(void* id128);
