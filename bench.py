@@ -576,9 +576,12 @@ def run_ours(args):
                 assert n_out == nS, f"e2e result count {n_out} != {nS}"
                 if it >= 2:
                     ts.append(dt)
-            e2e_s = sum(ts) / len(ts)
+            # median: the upload shares the host's PCIe root / memory system with whatever else runs on the box (observed: the
+            # same call between 273 ms and 1.1 s on different boxes); all steps are listed in ms_each
+            e2e_s = sorted(ts)[len(ts) // 2]
             e2e = {"value": (nR + nS) / e2e_s, "unit": "tuples/s", "h2d_bytes_per_step": 12 * (nR + nS),
-                   "d2h_bytes_per_step": 56 * world, "ms_per_step": e2e_s * 1e3, "steps": len(ts), "ms_each": [round(x * 1e3, 3) for x in ts],
+                   "d2h_bytes_per_step": 56 * world, "ms_per_step": e2e_s * 1e3, "steps": len(ts), "statistic": "median of the steps", "ms_mean": sum(ts) / len(ts) * 1e3,
+                   "ms_each": [round(x * 1e3, 3) for x in ts],
                    "h2d_gbs_if_the_copy_were_everything": 12 * (nR + nS) / e2e_s / 1e9,
                    "call": "hj3d_join_host" if world == 1 else "hj3d_exchange_begin_host x2 -> hj3d_exchange_end / hj3d_table_build_parts / hj3d_probe_parts on every rank",
                    "note": ("pinned host relations -> counters on the host, wall clock" + (", max over ranks" if world > 1 else "") + ".  The probe relation is "
@@ -948,7 +951,7 @@ def main():
     ap.add_argument("--log2-build", type=int, default=27)
     ap.add_argument("--log2-probe", type=int, default=30)
     ap.add_argument("--ref-log2-build", type=int, default=22, help="sample size of the CPU reference legs")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-plans", action="store_true", help="skip the secondary measurement of the other plans (N=1)")
