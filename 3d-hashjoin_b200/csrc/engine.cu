@@ -261,55 +261,31 @@ int make_contiguous(hj3d_ctx* c, Src* src, const PartsView* pre) {
   return HJ3D_OK;
 }
 
-// Partition `src` into the F fine bucket ranges of width Wf (one level if F <= 1024, else coarse
-// partitions of P2 consecutive fine ones first).  *ok = false: not representable (caller falls back).
-template <int HASH, bool LEFTID>
-int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
-                   Partitioned<typename HashT<HASH>::key_t>* fine_out, bool* ok, const PartsView* pre = nullptr) {
+// One refinement pass: every partition of `in` (bucket ranges of `fan` x Wout buckets, or segments of such ranges) is split
+// into `fan` consecutive ranges of Wout buckets; `out` gets n_out = (#ranges of in) x fan partitions.  F_real = how many of
+// them can hold records (sizes the fixed regions).  The ids stored in the records are final (left ids / row ids): the pass
+// just carries them (LEFTID + RECS).
+template <int HASH>
+int refine_partitions(hj3d_ctx* c, const Partitioned<typename HashT<HASH>::key_t>& in, Dir dir, uint32_t fan, uint32_t Wout, uint32_t n_out,
+                      uint64_t F_real, uint64_t n, Partitioned<typename HashT<HASH>::key_t>* out_) {
   using KeyT = typename HashT<HASH>::key_t;
-  Partitioned<KeyT>& fine = *fine_out;
-  const uint64_t n = src.n;
-  const uint32_t nl = dir.n_local;
-  *ok = true;
-  if (!pre && F <= (uint32_t)kMaxParts) {
-    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, F, Wf, 0, &fine)));
-    return HJ3D_OK;
-  }
-  // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
-  uint32_t P2 = 32;
-  uint64_t wc;
-  Partitioned<KeyT> coarse;
-  uint32_t P1;
-  if (pre) {   // level 1 happened elsewhere (the exchange): the coarse ranges are given, as segments
-    wc = pre->range_width;
-    if (wc == 0 || wc % Wf != 0 || wc / Wf > (uint64_t)kMaxParts) { *ok = false; return HJ3D_OK; }
-    P2 = (uint32_t)(wc / Wf);
-    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
-    coarse.recs = (Slot<KeyT>*)src.base; coarse.part_start = const_cast<unsigned long long*>(pre->seg_start);
-    coarse.counts = const_cast<unsigned long long*>(pre->seg_count); coarse.P = pre->n_seg; coarse.n_kept = n;
-  } else {
-    while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
-    wc = (uint64_t)Wf * P2;
-    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
-    if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { *ok = false; return HJ3D_OK; }
-    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, P1, (uint32_t)wc, 0, &coarse)));
-  }
+  Partitioned<KeyT>& fine = *out_;
   uint2* tm = nullptr; uint32_t n_tiles = 0;
   const int kTile = (int)c->part_threads * PartCfg<KeyT>::kItems;
-  HJ_TRY(make_tilemap(c, coarse, kTile, &tm, &n_tiles));
+  HJ_TRY(make_tilemap(c, in, kTile, &tm, &n_tiles));
   PhaseTimer pt(c, PH_PARTITION);
-  const uint32_t Fall = P1 * P2;                 // fine ids past F stay empty
-  const unsigned long long cap2 = (n / F + n / (16ull * F) + 2048) & ~1ull;
+  const uint32_t Fall = n_out;                    // ids past the directory stay empty
+  const unsigned long long cap2 = (n / F_real + n / (16ull * F_real) + 2048) & ~1ull;
   fine.P = Fall;
-  const PartFn pf = make_partfn(Wf, dir.lo, dir.n_local);
-  Src rs = records_src(coarse);
+  const PartFn pf = make_partfn(Wout, dir.lo, dir.n_local);
+  Src rs = records_src(in);
   bool planned = n_tiles > 0 && (c->part_sample == 2 || (c->part_sample == 1 && c->seen_skew));
   HJ_TRY(dev_alloc(c, &fine.part_start, (uint64_t)Fall + 1));
   HJ_TRY(dev_alloc(c, &fine.counts, Fall));
   unsigned long long total2 = (unsigned long long)Fall * cap2;
   if (planned) {
     const uint32_t stride = n_tiles >= 4096 ? 8u : (n_tiles >= 256 ? 2u : 1u);
-    HJ_TRY((plan_regions<HASH>(c, rs, true, tm, (uint32_t)kTile, n_tiles, stride, dir, pf, Fall, P2, coarse.n_kept, cap2,
+    HJ_TRY((plan_regions<HASH>(c, rs, true, tm, (uint32_t)kTile, n_tiles, stride, dir, pf, Fall, fan, in.n_kept, cap2,
                                fine.part_start, &total2)));
     if (total2 >= 0xFFFFFFF0ull) { planned = false; total2 = (unsigned long long)Fall * cap2; }
   }
@@ -318,9 +294,8 @@ int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
   }
   HJ_TRY(dev_alloc(c, &fine.recs, total2));
   CUDA_TRY(cudaMemsetAsync(fine.counts, 0, (size_t)Fall * 8, c->stream));
-  // the ids stored in the coarse records are final (left ids / row ids): level 2 just carries them (LEFTID + RECS)
   CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, dir, pf,
-                                            Fall, P2, 0, planned ? 0ull : cap2, fine.part_start, fine.counts, fine.recs)));
+                                            Fall, fan, 0, planned ? 0ull : cap2, fine.part_start, fine.counts, fine.recs)));
   unsigned long long* d_mx = c->d_scalar;
   CUDA_TRY(cudaMemsetAsync(d_mx, 0, 16, c->stream));
   k_part_overflow<<<64, 256, 0, c->stream>>>(fine.counts, fine.part_start, Fall, d_mx);
@@ -337,11 +312,58 @@ int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
     HJ_TRY((run_scan<unsigned long long, false>(c, LoadU64{fine.counts}, StoreExU64{fine.part_start}, Fall, (DevStats*)nullptr, (unsigned long long*)nullptr)));
     CUDA_TRY(cudaMemsetAsync(counts2, 0, (size_t)Fall * 8, c->stream));
     CUDA_TRY((launch_part_scatter<HASH, true>(c->stream, true, (int)c->part_threads, c->part_rank_match != 0, n_tiles, rs, tm, dir, pf,
-                                              Fall, P2, 0, ~0ull, fine.part_start, counts2, fine.recs)));
+                                              Fall, fan, 0, ~0ull, fine.part_start, counts2, fine.recs)));
     ++c->launches;
   }
   CUDA_TRY(cudaGetLastError());
   return HJ3D_OK;
+}
+
+// Partition `src` into the F fine bucket ranges of width Wf (one level if F <= 1024, else coarse
+// partitions of P2 consecutive fine ones first).  *ok = false: not representable (caller falls back).
+// `pre`: level 1 happened elsewhere (the exchange) and the coarse ranges are given as segments; a range that holds more
+// than 1024 fine partitions (heavily duplicated keys: narrow fine partitions) is refined in two passes.
+template <int HASH, bool LEFTID>
+int partition_fine(hj3d_ctx* c, Src src, Dir dir, uint32_t Wf, uint32_t F,
+                   Partitioned<typename HashT<HASH>::key_t>* fine_out, bool* ok, const PartsView* pre = nullptr) {
+  using KeyT = typename HashT<HASH>::key_t;
+  const uint64_t n = src.n;
+  const uint32_t nl = dir.n_local;
+  *ok = true;
+  if (!pre && F <= (uint32_t)kMaxParts) {
+    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, F, Wf, 0, fine_out)));
+    return HJ3D_OK;
+  }
+  // two levels: coarse partitions of P2 consecutive fine partitions, then fine inside each coarse region
+  uint32_t P2 = 32;
+  uint64_t wc;
+  Partitioned<KeyT> coarse;
+  uint32_t P1;
+  if (pre) {
+    wc = pre->range_width;
+    if (wc == 0 || wc % Wf != 0 || wc / Wf > (uint64_t)kMaxParts * kMaxParts) { *ok = false; return HJ3D_OK; }
+    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+    if ((uint64_t)P1 * (wc / Wf) > 0x7FFFFFFFull) { *ok = false; return HJ3D_OK; }
+    P2 = (uint32_t)(wc / Wf);
+    coarse.recs = (Slot<KeyT>*)src.base; coarse.part_start = const_cast<unsigned long long*>(pre->seg_start);
+    coarse.counts = const_cast<unsigned long long*>(pre->seg_count); coarse.P = pre->n_seg; coarse.n_kept = n;
+    if (P2 > (uint32_t)kMaxParts) {
+      if (P2 & (P2 - 1)) { *ok = false; return HJ3D_OK; }
+      uint32_t P2a = 1; while ((uint64_t)P2a * P2a < P2) P2a <<= 1;        // ranges -> P2a mid ranges -> P2b fine partitions each
+      const uint32_t P2b = P2 / P2a;
+      Partitioned<KeyT> mid;
+      const uint64_t F_mid = ((uint64_t)F + P2b - 1) / P2b;
+      HJ_TRY((refine_partitions<HASH>(c, coarse, dir, P2a, Wf * P2b, P1 * P2a, F_mid ? F_mid : 1, n, &mid)));
+      return refine_partitions<HASH>(c, mid, dir, P2b, Wf, P1 * P2, F, n, fine_out);
+    }
+  } else {
+    while ((uint64_t)P2 * P2 < F && P2 < (uint32_t)kMaxParts) P2 <<= 1;
+    wc = (uint64_t)Wf * P2;
+    P1 = (uint32_t)(((uint64_t)nl + wc - 1) / wc);
+    if (P1 > (uint32_t)kMaxParts || wc > 0xFFFFFFFFull) { *ok = false; return HJ3D_OK; }
+    HJ_TRY((partition_local<HASH, LEFTID>(c, src, dir, P1, (uint32_t)wc, 0, &coarse)));
+  }
+  return refine_partitions<HASH>(c, coarse, dir, P2, Wf, P1 * P2, F, n, fine_out);
 }
 
 // fine partitions: as many consecutive buckets as fit in shared memory together with their slots / groups
@@ -712,7 +734,10 @@ int plan_probe(hj3d_ctx* c, hj3d_table* t, Src src, ProbePlan<typename HashT<HAS
   if (pre) {   // pre-partitioned input: only the fine-partition path continues from the given coarse ranges
     const bool fine_path = c->smem_probe && t->fine_width && (int64_t)src.n >= c->smem_min_probe && t->fine_parts > 1 &&
                            (double)src.n * 1.08 + 4096.0 * (double)t->fine_parts < 4.0e9 &&
-                           pre->range_width % t->fine_width == 0 && pre->range_width / t->fine_width <= (uint32_t)kMaxParts;
+                           pre->range_width % t->fine_width == 0 &&
+                           (pre->range_width / t->fine_width <= (uint32_t)kMaxParts ||            // more: two refinement passes (powers of two)
+                            (pre->range_width / t->fine_width <= (uint32_t)kMaxParts * (uint32_t)kMaxParts &&
+                             ((pre->range_width / t->fine_width) & (pre->range_width / t->fine_width - 1)) == 0));
     if (!fine_path) { HJ_TRY(make_contiguous<KeyT>(c, &src, pre)); pre = nullptr; }
   }
   pl->src = src;

@@ -625,3 +625,69 @@ def test_hot_key_probe_replication(pkg, oracle, world):
         cm.destroy()
     for c in ctxs:
         c.close()
+
+
+def test_exchanged_ranges_of_more_than_1024_fine_partitions(pkg, oracle):
+    """Exchange ranges so wide (2^19 buckets) that one holds 2048+ fine partitions of the table: the local join refines them in
+    two passes instead of compacting and re-partitioning (engine.cu, partition_fine / refine_partitions).  Build and probe
+    from exchanged parts, chaining on unique keys and the nested table on 8 duplicates per key."""
+    import torch
+    import ctypes as C
+    lib = pkg.capi.load()
+    rng = np.random.default_rng(901)
+    world, D = 2, 1 << 20
+    nR, nS = 1 << 20, 1 << 21
+    R = np.zeros((nR, 3), np.uint32); R[:, 0] = rng.permutation(nR)
+    S = np.zeros((nS, 3), np.uint32); S[:, 0] = np.arange(nS); S[:, 1] = rng.integers(0, nR // 4, nS)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctxs = [pkg.Context(0, stream=stream) for _ in range(world)]
+    for c in ctxs:
+        c.set_option(pkg.OPT_SMEM_MIN_PROBE, 0); c.set_option(pkg.OPT_SMEM_SLICE_BYTES, 4096)
+        c.set_option(pkg.capi.OPT_SMEM_BUILD_BYTES, 4096); c.set_option(pkg.OPT_SMEM_CHUNK, 4096)
+    comms = pkg.Comm.local(ctxs)
+    for cm in comms:
+        cm.set_option(pkg.capi.XOPT_MIN_RANGE_WIDTH, 1 << 19)
+        cm.set_option(pkg.capi.XOPT_TARGET_RANGES, 2)
+    sl = lambda n, r: (r * n // world, (r + 1) * n // world)
+    for mode in (1, 3):
+        B, kb, P, kp = (R, 0, S, 4) if mode == 1 else (S, 4, R, 0)
+        o = oracle_plan(oracle, pyo, mode, B, pyo.KeySpec(12, kb), D, P, pyo.KeySpec(12, kp))
+        nB, nP = len(B), len(P)
+        for cm in comms:
+            cm.reserve(0, int(nB * 1.3 / world) + 70000, 4)
+            cm.reserve(1, int(nP * 1.3 / world) + 70000, 4)
+        dB, dP = to_dev(B).view(-1, 12), to_dev(P).view(-1, 12)
+        slices = []
+        for r, cm in enumerate(comms):
+            b0, b1 = sl(nB, r); p0, p1 = sl(nP, r)
+            tb, tp = dB[b0:b1].contiguous(), dP[p0:p1].contiguous()
+            slices.append((tb, b0, tp, p0))
+            cm.begin(0, tb, b1 - b0, KSg(pkg, 12, kb), D, b0)
+            cm.begin(1, tp, p1 - p0, KSg(pkg, 12, kp), D, p0)
+        parts = (pkg.Stats * world)()
+        tot = {"matches": 0, "num_cmps": 0, "out_tuples": 0, "checksum_sum": 0, "checksum_xor": 0}
+        for r, cm in enumerate(comms):
+            tb, b0, tp, p0 = slices[r]
+            rc, pb = cm.end(0, tb, b0, nB); assert rc == 0
+            rc, pp = cm.end(1, tp, p0, nP); assert rc == 0
+            lo, hi = cm.shard(D)
+            t = ctxs[r].table(pkg.CHAINING if mode <= 1 else pkg.NESTED, D, shard=(lo, hi))
+            t.build_parts(pb)
+            tm = ctxs[r].timings()
+            assert tm["partition_ms"] > 0 and tm["histogram_ms"] == 0, "the build did not continue from the exchanged ranges (global-memory build instead)"
+            _, c1, u1 = t.probe_parts(pp, mode, flags=pkg.F_CHECKSUM)
+            res = u1 if mode == 3 else c1
+            tot["matches"] += c1["matches"]; tot["num_cmps"] += c1["num_cmps"]; tot["out_tuples"] += res["out_tuples"]
+            tot["checksum_sum"] = (tot["checksum_sum"] + res["checksum_sum"]) & ((1 << 64) - 1); tot["checksum_xor"] ^= res["checksum_xor"]
+            parts[r] = pkg.Stats(**t.stats())
+            t.destroy(); pb.destroy(); pp.destroy()
+        merged = pkg.Stats()
+        lib.hj3d_stats_merge(parts, world, C.byref(merged))
+        ref_res = o["unnest"] if mode == 3 else o["probe"]
+        assert merged.as_dict() == o["stats"], mode
+        assert tot["matches"] == o["probe"]["matches"] and tot["num_cmps"] == o["probe"]["num_cmps"], mode
+        assert (tot["out_tuples"], tot["checksum_sum"], tot["checksum_xor"]) == (ref_res["out_tuples"], ref_res["checksum_sum"], ref_res["checksum_xor"]), mode
+    for cm in comms:
+        cm.destroy()
+    for c in ctxs:
+        c.close()
