@@ -142,3 +142,21 @@ def test_algebra_example_prints_reference_results_in_reference_order():
     joined = "(1,11,1,-1)\n(1,11,1,-3)\n(1,11,1,-2)\n(2,21,2,-1)\n(2,21,2,-2)\n(3,31,3,-1)\n"
     assert joined in t["test2"] and "AlgUnnest|6|" in t["test2"] and "AlgTop|6|" in t["test2"] and "AlgNestJoinProbe|3|" in t["test2"]
     assert joined in t["test3"] and "AlgHashJoinProbe|6|" in t["test3"] and "sizeof(Node) 24" in t["test3"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cli", [["-R", "14", "-S", "18", "-g", "3", "-p", "Csr"], ["-R", "14", "-S", "17", "-g", "2", "-p", "Nsr"],
+                                 ["-R", "14", "-S", "18", "-g", "4", "-p", "Csr", "--skew"], ["-R", "13", "-S", "18", "-g", "2", "-p", "Nsr", "--skew"]])
+def test_sharded_example_driver(cli):
+    """drivers/main_sharded_example.cc: a C++ host that owns all ranks in one process, C ABI only: host relations streamed
+    through the exchange (uniform) or hot-key probe replication (--skew); merged counters, checksum and HtStatistics must
+    equal the unsharded hj3d_join_host result (the driver exits non-zero otherwise)."""
+    build_drivers()
+    r = subprocess.run([os.path.join(DRV, "main_sharded_example.out"), *cli], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    hdr, row = [l.split(";") for l in r.stdout.strip().split("\n")[-2:]]
+    rec = dict(zip(hdr, row))
+    assert rec["sharded_equals_unsharded"] == "yes" and int(rec["c_top"]) == 1 << int(cli[3])
+    if "--skew" in cli:
+        assert int(rec["hot_tuples_kept_local"]) > 0
+
