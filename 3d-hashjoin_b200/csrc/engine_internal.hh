@@ -142,6 +142,10 @@ struct hj3d_parts {
   struct hj3d_comm* comm = nullptr;
   int      slot = 0;
   int      hot_mode = -1;                // probe mode the answers were computed for (hj3d_parts_hot_answers)
+  hj3d_parts() = default;
+  hj3d_parts(const hj3d_parts&) = delete;
+  hj3d_parts& operator=(const hj3d_parts&) = delete;
+  ~hj3d_parts() { cudaFree(d_start); cudaFree(d_count); }   // the segment tables are the only memory a parts object owns
 };
 
 struct PhaseTimer {

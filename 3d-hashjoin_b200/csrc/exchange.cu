@@ -805,7 +805,6 @@ int hj3d_parts_info(hj3d_parts* p, uint64_t* n_records, uint64_t* n_sent_remote,
 
 int hj3d_parts_destroy(hj3d_parts* p) {
   if (!p) return HJ3D_OK;
-  cudaFree(p->d_start); cudaFree(p->d_count);
   delete p;
   return HJ3D_OK;
 }
