@@ -62,6 +62,15 @@ def test_drivers_fail_loudly_without_gpu(tmp_path):
     assert r.returncode != 0 and "hj3d" in r.stderr          # no CPU fallback behind the operator templates
 
 
+def test_sharded_example_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    build_drivers()
+    r = subprocess.run([os.path.join(DRV, "main_sharded_example.out"), "-R", "8", "-S", "10", "-g", "2"], capture_output=True, text=True)
+    assert r.returncode == 3 and "hj3d" in r.stderr and "CPU fallback" in r.stderr     # hj3d_ctx_create's own message
+
+
 def read_csv(path):
     rows = list(csv.reader(open(path), delimiter=";"))
     return rows[0], rows[1:]
